@@ -1,0 +1,15 @@
+"""osml_b200 -- B200-native brute-force weighted kNN predict behind ViktorC/OSML's model API.
+
+Only the path BASELINE.json's north_star names is here: ``KNearestNeighborsRegression`` and
+``KNearestNeighborsClassification`` (osml/predict.py:721-811 of the reference) with the reference's
+``fit / predict / evaluate / test`` contract, computed by hand-written sm_100a CUDA kernels behind the C ABI of
+``include/osml_knn.h``.  There is no CPU fallback: without the built library and a CUDA device ``fit`` raises.
+"""
+from osml_b200.model import Model, load, save, is_categorical, is_continuous  # noqa: F401
+from osml_b200.predict import (  # noqa: F401
+    ClassificationModel, KNearestNeighbors, KNearestNeighborsClassification, KNearestNeighborsRegression,
+    PredictiveModel, RegressionModel)
+
+__all__ = ['Model', 'PredictiveModel', 'RegressionModel', 'ClassificationModel', 'KNearestNeighbors',
+           'KNearestNeighborsRegression', 'KNearestNeighborsClassification', 'save', 'load', 'is_continuous',
+           'is_categorical']

@@ -1,0 +1,196 @@
+"""ctypes binding of the C ABI in include/osml_knn.h (libosml_knn.so, built in-tree by osml_b200/build.py).
+
+This is the only door to the arithmetic of the path.  It fails loudly: a missing library raises ImportError with the
+build command, a non-zero status raises ValueError (where the reference raises ValueError) or RuntimeError.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libosml_knn.so')
+
+OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4
+ROW_MAJOR, COL_MAJOR = 0, 1
+SUM_PAIRWISE, SUM_SEQUENTIAL = 0, 1
+REGRESSION, CLASSIFICATION = 0, 1
+PATH_AUTO, PATH_DIRECT, PATH_TENSOR = 0, 1, 2
+PATHS = {'auto': PATH_AUTO, 'direct': PATH_DIRECT, 'tensor': PATH_TENSOR}
+
+DTYPE_CODES = {
+    np.dtype(np.float32): 0, np.dtype(np.float64): 1,
+    np.dtype(np.int8): 2, np.dtype(np.int16): 3, np.dtype(np.int32): 4, np.dtype(np.int64): 5,
+    np.dtype(np.uint8): 6, np.dtype(np.uint16): 7, np.dtype(np.uint32): 8, np.dtype(np.uint64): 9,
+}
+
+# every symbol include/osml_knn.h declares; tests/test_abi.py checks the header against this table
+SYMBOLS = ('osml_knn_create', 'osml_knn_destroy', 'osml_knn_predict', 'osml_knn_predict_device',
+           'osml_knn_neighbours_device', 'osml_knn_merge_predict_device', 'osml_knn_set_option',
+           'osml_knn_get_stats', 'osml_knn_reset_stats', 'osml_knn_describe', 'osml_knn_last_error',
+           'osml_knn_abi_version')
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [('kernel_launches', ctypes.c_int64), ('queries', ctypes.c_int64),
+                ('fallback_queries', ctypes.c_int64), ('tensor_queries', ctypes.c_int64),
+                ('last_filter_ms', ctypes.c_double), ('last_total_ms', ctypes.c_double),
+                ('last_filter_launches', ctypes.c_int64), ('device_bytes', ctypes.c_int64)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Loads libosml_knn.so once.  No fallback: raises ImportError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('%s is missing: build it with `python -m osml_b200.build` (nvcc, sm_100a). '
+                          'osml_b200 has no CPU fallback.' % LIB_PATH)
+    cdll = ctypes.CDLL(LIB_PATH)
+    c_i64, c_int, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+    cdll.osml_knn_create.argtypes = [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp, c_int,
+                                     c_i64, c_i64, c_int, c_dbl, c_int, c_dbl]
+    cdll.osml_knn_destroy.argtypes = [c_vp]
+    cdll.osml_knn_predict.argtypes = [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp]
+    cdll.osml_knn_predict_device.argtypes = [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]
+    cdll.osml_knn_neighbours_device.argtypes = [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]
+    cdll.osml_knn_merge_predict_device.argtypes = [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]
+    cdll.osml_knn_set_option.argtypes = [c_vp, ctypes.c_char_p, c_dbl]
+    cdll.osml_knn_get_stats.argtypes = [c_vp, ctypes.POINTER(Stats)]
+    cdll.osml_knn_reset_stats.argtypes = [c_vp]
+    cdll.osml_knn_describe.argtypes = [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_int),
+                                       ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    cdll.osml_knn_last_error.restype = ctypes.c_char_p
+    cdll.osml_knn_last_error.argtypes = []
+    cdll.osml_knn_abi_version.argtypes = []
+    for name in SYMBOLS:
+        if name not in ('osml_knn_last_error',):
+            getattr(cdll, name).restype = c_int
+    _lib = cdll
+    return _lib
+
+
+def check(status):
+    """Maps a status to the reference's exception types."""
+    if status == OK:
+        return
+    message = lib().osml_knn_last_error().decode('utf-8', 'replace')
+    if status == EINVAL:
+        raise ValueError(message)
+    if status == EUNSUPPORTED:
+        raise NotImplementedError(message)
+    if status == ENOMEM:
+        raise MemoryError(message)
+    raise RuntimeError('osml_knn: ' + message)
+
+
+def dtype_code(dtype):
+    try:
+        return DTYPE_CODES[np.dtype(dtype)]
+    except KeyError:
+        raise NotImplementedError('dtype %s is not supported by the GPU kNN path' % dtype)
+
+
+def matrix_layout(values):
+    """(contiguous array, layout code) for a 2-D host matrix, copying only when it is neither C nor F contiguous."""
+    if values.flags['C_CONTIGUOUS']:
+        return values, ROW_MAJOR
+    if values.flags['F_CONTIGUOUS']:
+        return values, COL_MAJOR
+    return np.ascontiguousarray(values), ROW_MAJOR
+
+
+def sum_order_of(values):
+    """Order in which numpy's ``sum(axis=1)`` adds the squared differences of ``values - q`` (predict.py:742): the
+    subtraction result inherits the stride order of ``values``; feature by feature when axis 0 is the fast axis (the
+    F-ordered ``DataFrame.values`` of pandas 3), numpy's pairwise tree when axis 1 is."""
+    n, d = values.shape
+    if d == 1 or n == 1:
+        return SUM_SEQUENTIAL
+    s0, s1 = (abs(s) for s in values.strides)
+    return SUM_SEQUENTIAL if s0 <= s1 else SUM_PAIRWISE
+
+
+class Index:
+    """Owner of one ``osml_knn_index`` handle."""
+
+    def __init__(self, train, labels, k, rbf_gamma, epsilon, device=0, index_base=0, sum_order=None,
+                 gamma_is_f32=False):
+        self._handle = ctypes.c_void_p()
+        train = np.asarray(train)
+        labels = np.ascontiguousarray(labels)
+        if train.ndim != 2:
+            raise ValueError
+        if sum_order is None:
+            sum_order = sum_order_of(train)
+        mat, layout = matrix_layout(train)
+        self.dtype = mat.dtype
+        self.k = int(k)
+        self.n, self.d = int(mat.shape[0]), int(mat.shape[1])
+        self.dist_dtype = np.dtype(np.float32) if mat.dtype == np.float32 else np.dtype(np.float64)
+        self.device = int(device)
+        check(lib().osml_knn_create(ctypes.byref(self._handle), self.device, mat.ctypes.data, dtype_code(mat.dtype),
+                                    layout, self.n, self.d, int(sum_order), labels.ctypes.data,
+                                    dtype_code(labels.dtype), int(labels.shape[0]), int(index_base), self.k,
+                                    float(rbf_gamma), int(bool(gamma_is_f32)), float(epsilon)))
+
+    def close(self):
+        if getattr(self, '_handle', None) is not None and self._handle.value:
+            lib().osml_knn_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        check(lib().osml_knn_set_option(self._handle, name.encode(), float(value)))
+
+    def stats(self):
+        st = Stats()
+        check(lib().osml_knn_get_stats(self._handle, ctypes.byref(st)))
+        return st.as_dict()
+
+    def reset_stats(self):
+        check(lib().osml_knn_reset_stats(self._handle))
+
+    def predict(self, queries, task, return_neighbours=False):
+        """Host buffers in, host buffers out (osml_knn_predict)."""
+        queries = np.asarray(queries)
+        if queries.ndim != 2 or queries.shape[1] != self.d or queries.dtype != self.dtype:
+            raise ValueError
+        mat, layout = matrix_layout(queries)
+        q = int(mat.shape[0])
+        pred = np.empty(q, dtype=np.float64)
+        idx = dist = None
+        idx_p = dist_p = None
+        if return_neighbours:
+            idx = np.empty((q, self.k + 1), dtype=np.int64)
+            dist = np.empty((q, self.k + 1), dtype=self.dist_dtype)
+            idx_p, dist_p = idx.ctypes.data, dist.ctypes.data
+        check(lib().osml_knn_predict(self._handle, mat.ctypes.data, layout, q, int(task), pred.ctypes.data, idx_p,
+                                     dist_p))
+        if return_neighbours:
+            return pred, idx, dist
+        return pred
+
+    # device-pointer entry points (raw addresses: torch ``tensor.data_ptr()`` or any CUDA allocation) -------------
+    def predict_device(self, d_queries, q, task, d_out_pred, d_out_idx=None, d_out_dist=None, stream=None):
+        check(lib().osml_knn_predict_device(self._handle, d_queries, int(q), int(task), d_out_pred, d_out_idx,
+                                            d_out_dist, stream))
+
+    def neighbours_device(self, d_queries, q, d_out_idx, d_out_dist, stream=None):
+        check(lib().osml_knn_neighbours_device(self._handle, d_queries, int(q), d_out_idx, d_out_dist, stream))
+
+    def merge_predict_device(self, d_part_idx, d_part_dist, parts, q, task, d_out_pred, d_out_idx=None,
+                             d_out_dist=None, stream=None):
+        check(lib().osml_knn_merge_predict_device(self._handle, d_part_idx, d_part_dist, int(parts), int(q),
+                                                  int(task), d_out_pred, d_out_idx, d_out_dist, stream))

@@ -1,0 +1,521 @@
+// C ABI of the kNN predict path (include/osml_knn.h): index lifetime, host <-> device staging, kernel dispatch.
+// No torch types, no CPU fallback: every arithmetic step of the path runs in the CUDA kernels of this directory.
+#include "../../include/osml_knn.h"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "knn_aggregate.cuh"
+#include "knn_common.cuh"
+#include "knn_direct.cuh"
+#include "knn_tensor.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t err__ = (expr);                                                                         \
+        if (err__ != cudaSuccess) {                                                                         \
+            cudaGetLastError();                                                                             \
+            return fail(err__ == cudaErrorMemoryAllocation ? OSML_KNN_ENOMEM : OSML_KNN_ECUDA,              \
+                        std::string(#expr) + ": " + cudaGetErrorString(err__));                            \
+        }                                                                                                   \
+    } while (0)
+
+size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case OSML_KNN_F32: case OSML_KNN_I32: case OSML_KNN_U32: return 4;
+        case OSML_KNN_F64: case OSML_KNN_I64: case OSML_KNN_U64: return 8;
+        case OSML_KNN_I8: case OSML_KNN_U8: return 1;
+        case OSML_KNN_I16: case OSML_KNN_U16: return 2;
+        default: return 0;
+    }
+}
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+// tiled transpose of a column-major (n x d, element (i, j) at j * n + i) matrix into row-major, by element size
+template <typename W>
+__global__ void transpose_colmajor_kernel(const W* __restrict__ in, W* __restrict__ out, int64_t n, int64_t d) {
+    __shared__ W tile[32][33];
+    const int64_t i0 = (int64_t)blockIdx.x * 32, j0 = (int64_t)blockIdx.y * 32;
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int64_t i = i0 + threadIdx.x, j = j0 + jj;
+        if (i < n && j < d) tile[jj][threadIdx.x] = in[j * n + i];
+    }
+    __syncthreads();
+    for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
+        const int64_t i = i0 + ii, j = j0 + threadIdx.x;
+        if (i < n && j < d) out[i * d + j] = tile[threadIdx.x][ii];
+    }
+}
+
+}  // namespace
+
+struct osml_knn_index {
+    int device = 0;
+    int dtype = 0;
+    int64_t n = 0, d = 0;
+    int sum_order = 1;
+    int k = 0;
+    double gamma = 1.0;
+    int gamma_is_f32 = 0;
+    double epsilon = 1e-8;
+    int64_t index_base = 0;
+    int64_t n_labels = 0;
+    int label_kind = 0;
+    int path = OSML_KNN_PATH_AUTO;
+    int slack = -1;
+    int64_t query_block = 0;
+
+    DeviceBuffer train;        // row-major n x d, original dtype
+    DeviceBuffer label_bits;   // int64 per label
+    DeviceBuffer stage;        // raw upload staging (column-major inputs)
+    DeviceBuffer queries;      // row-major q x d
+    DeviceBuffer part_d, part_i;   // K2 partial lists
+    DeviceBuffer nn_d, nn_i;       // final lists
+    DeviceBuffer pred;
+    osml::TensorState tensor;  // K0/K1/K3 state (bf16 copy, norms, tensor maps, scratch)
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    osml_knn_stats stats{};
+
+    size_t dist_size() const { return dtype == OSML_KNN_F32 ? 4 : 8; }
+    int ksel() const { return k + 1; }
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int upload_matrix(osml_knn_index* ix, const void* host, int layout, int64_t rows, int64_t cols, DeviceBuffer& dst,
+                  cudaStream_t stream) {
+    const size_t es = dtype_size(ix->dtype);
+    const size_t bytes = (size_t)rows * cols * es;
+    CUDA_TRY(dst.reserve(bytes));
+    if (layout == OSML_KNN_ROW_MAJOR || rows == 1 || cols == 1) {
+        CUDA_TRY(cudaMemcpyAsync(dst.ptr, host, bytes, cudaMemcpyHostToDevice, stream));
+        return OSML_KNN_OK;
+    }
+    CUDA_TRY(ix->stage.reserve(bytes));
+    CUDA_TRY(cudaMemcpyAsync(ix->stage.ptr, host, bytes, cudaMemcpyHostToDevice, stream));
+    dim3 block(32, 8), grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+    switch (es) {
+        case 1: transpose_colmajor_kernel<uint8_t><<<grid, block, 0, stream>>>(ix->stage.as<uint8_t>(), dst.as<uint8_t>(), rows, cols); break;
+        case 2: transpose_colmajor_kernel<uint16_t><<<grid, block, 0, stream>>>(ix->stage.as<uint16_t>(), dst.as<uint16_t>(), rows, cols); break;
+        case 4: transpose_colmajor_kernel<uint32_t><<<grid, block, 0, stream>>>(ix->stage.as<uint32_t>(), dst.as<uint32_t>(), rows, cols); break;
+        default: transpose_colmajor_kernel<uint64_t><<<grid, block, 0, stream>>>(ix->stage.as<uint64_t>(), dst.as<uint64_t>(), rows, cols); break;
+    }
+    ix->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return OSML_KNN_OK;
+}
+
+template <typename T>
+int labels_to_bits(const void* labels, int64_t n, std::vector<int64_t>& out) {
+    const T* p = static_cast<const T*>(labels);
+    out.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) out[(size_t)i] = (int64_t)p[i];
+    return 0;
+}
+
+int convert_labels(const void* labels, int label_dtype, int64_t n, std::vector<int64_t>& out, int* kind) {
+    switch (label_dtype) {
+        case OSML_KNN_I8: *kind = osml::kLabelSigned; return labels_to_bits<int8_t>(labels, n, out);
+        case OSML_KNN_I16: *kind = osml::kLabelSigned; return labels_to_bits<int16_t>(labels, n, out);
+        case OSML_KNN_I32: *kind = osml::kLabelSigned; return labels_to_bits<int32_t>(labels, n, out);
+        case OSML_KNN_I64: *kind = osml::kLabelSigned; return labels_to_bits<int64_t>(labels, n, out);
+        case OSML_KNN_U8: *kind = osml::kLabelUnsigned; return labels_to_bits<uint8_t>(labels, n, out);
+        case OSML_KNN_U16: *kind = osml::kLabelUnsigned; return labels_to_bits<uint16_t>(labels, n, out);
+        case OSML_KNN_U32: *kind = osml::kLabelUnsigned; return labels_to_bits<uint32_t>(labels, n, out);
+        case OSML_KNN_U64: *kind = osml::kLabelUnsigned; return labels_to_bits<uint64_t>(labels, n, out);
+        case OSML_KNN_F32: {
+            *kind = osml::kLabelFloat;
+            const float* p = static_cast<const float*>(labels);
+            out.resize((size_t)n);
+            for (int64_t i = 0; i < n; ++i) { double v = (double)p[i]; std::memcpy(&out[(size_t)i], &v, 8); }
+            return 0;
+        }
+        case OSML_KNN_F64: {
+            *kind = osml::kLabelFloat;
+            out.resize((size_t)n);
+            std::memcpy(out.data(), labels, (size_t)n * 8);
+            return 0;
+        }
+        default: return 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K2 launch
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T, int TN, int DCH>
+int launch_direct_typed(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d, int64_t* out_i,
+                        cudaStream_t stream) {
+    using Dist = typename osml::Elem<T>::Dist;
+    const int ksel = ix->ksel();
+    const int n = (int)ix->n, d = (int)ix->d;
+    const int ctas_q = (int)((q + osml::kDirectQT - 1) / osml::kDirectQT);
+    const bool generic = osml::Elem<T>::kIsFloat && ix->sum_order == OSML_KNN_SUM_PAIRWISE && d > 1;
+    int nsplit = 1;
+    if (ctas_q < 296) {
+        nsplit = (296 + ctas_q - 1) / ctas_q;
+        const int max_split = std::max(1, n / (4 * TN));
+        nsplit = std::max(1, std::min(std::min(nsplit, 64), max_split));
+    }
+    int rows_per_split = (n + nsplit - 1) / nsplit;
+    rows_per_split = ((rows_per_split + TN - 1) / TN) * TN;
+    nsplit = (n + rows_per_split - 1) / rows_per_split;
+
+    Dist* part_d = static_cast<Dist*>(out_d);
+    int64_t* part_i = out_i;
+    if (nsplit > 1) {
+        CUDA_TRY(ix->part_d.reserve((size_t)q * nsplit * ksel * sizeof(Dist)));
+        CUDA_TRY(ix->part_i.reserve((size_t)q * nsplit * ksel * sizeof(int64_t)));
+        part_d = ix->part_d.as<Dist>();
+        part_i = ix->part_i.as<int64_t>();
+    }
+    dim3 grid((unsigned)ctas_q, (unsigned)nsplit);
+    if (generic) {
+        const size_t smem = (size_t)ksel * osml::kDirectQT * (sizeof(Dist) + sizeof(int));
+        auto kern = osml::knn_direct_generic_kernel<T>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, osml::kDirectQT, smem, stream>>>(ix->train.as<T>(), static_cast<const T*>(d_queries), n, d, (int)q,
+                                                      ksel, rows_per_split, ix->index_base, ix->sum_order, part_d,
+                                                      part_i);
+    } else {
+        const size_t smem = osml::DirectSmem<T, TN, DCH>::bytes(ksel);
+        auto kern = osml::knn_direct_seq_kernel<T, TN, DCH>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, osml::kDirectQT, smem, stream>>>(ix->train.as<T>(), static_cast<const T*>(d_queries), n, d, (int)q,
+                                                      ksel, rows_per_split, ix->index_base, part_d, part_i);
+    }
+    ix->stats.kernel_launches++;
+    ix->stats.last_filter_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (nsplit > 1) {
+        const int threads = 128;
+        osml::knn_merge_lists_kernel<Dist><<<(unsigned)((q + threads - 1) / threads), threads, 0, stream>>>(
+            part_d, part_i, nsplit, (int64_t)ksel, (int64_t)nsplit * ksel, q, ksel, static_cast<Dist*>(out_d), out_i);
+        ix->stats.kernel_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return OSML_KNN_OK;
+}
+
+int launch_direct(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d, int64_t* out_i,
+                  cudaStream_t stream) {
+    switch (ix->dtype) {
+        case OSML_KNN_F32: return launch_direct_typed<float, 32, 16>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_F64: return launch_direct_typed<double, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_I8: return launch_direct_typed<int8_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_I16: return launch_direct_typed<int16_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_I32: return launch_direct_typed<int32_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_I64: return launch_direct_typed<int64_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_U8: return launch_direct_typed<uint8_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_U16: return launch_direct_typed<uint16_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_U32: return launch_direct_typed<uint32_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_U64: return launch_direct_typed<uint64_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
+        default: return fail(OSML_KNN_EUNSUPPORTED, "unsupported dtype");
+    }
+}
+
+bool use_tensor_path(const osml_knn_index* ix, int64_t q) {
+    if (ix->path == OSML_KNN_PATH_DIRECT) return false;
+    if (!osml::tensor_path_supported(ix->dtype, ix->n, ix->d, ix->k)) return false;
+    if (ix->path == OSML_KNN_PATH_TENSOR) return true;
+    // auto: the filter pays off once the pair count dwarfs its fixed costs
+    return (double)ix->n * (double)q * (double)ix->d >= 2.0e11 && ix->n >= 16384;
+}
+
+// neighbour search into (out_d, out_i): final ascending lists, global indices
+int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d, int64_t* out_i,
+               cudaStream_t stream) {
+    if (q < 1) return fail(OSML_KNN_EINVAL, "no queries");
+    if (q > 0x7fffffff / 2) return fail(OSML_KNN_EUNSUPPORTED, "more than 2^30 queries in one call");
+    ix->stats.last_filter_launches = 0;
+    if (use_tensor_path(ix, q)) {
+        osml::TensorLaunch tl;
+        tl.train = ix->train.ptr; tl.dtype = ix->dtype; tl.n = ix->n; tl.d = ix->d; tl.k = ix->k;
+        tl.sum_order = ix->sum_order; tl.index_base = ix->index_base; tl.slack = ix->slack;
+        int64_t fallback = 0, launches = 0;
+        std::string err;
+        int rc = osml::tensor_neighbours(ix->tensor, tl, d_queries, q, out_d, out_i, stream, &fallback, &launches, &err,
+                                         [&](const void* dq, int64_t qq, void* od, int64_t* oi) {
+                                             return launch_direct(ix, dq, qq, od, oi, stream);
+                                         });
+        ix->stats.kernel_launches += launches;
+        ix->stats.last_filter_launches += launches;
+        if (rc != OSML_KNN_OK) return err.empty() ? rc : fail(rc, err);
+        ix->stats.fallback_queries += fallback;
+        ix->stats.tensor_queries += q;
+        return OSML_KNN_OK;
+    }
+    return launch_direct(ix, d_queries, q, out_d, out_i, stream);
+}
+
+int aggregate(osml_knn_index* ix, const void* nn_d, const int64_t* nn_i, int64_t q, int task, double* d_out_pred,
+              cudaStream_t stream) {
+    if (task != OSML_KNN_REGRESSION && task != OSML_KNN_CLASSIFICATION) return fail(OSML_KNN_EINVAL, "bad task");
+    const unsigned grid = (unsigned)((q + osml::kAggWarpsPerCta - 1) / osml::kAggWarpsPerCta);
+    const int threads = 32 * osml::kAggWarpsPerCta;
+    if (ix->dist_size() == 4) {
+        osml::knn_aggregate_kernel<float><<<grid, threads, 0, stream>>>(
+            static_cast<const float*>(nn_d), nn_i, q, ix->k, ix->label_bits.as<int64_t>(), ix->label_kind, ix->n_labels,
+            ix->gamma, ix->gamma_is_f32, ix->epsilon, task, d_out_pred);
+    } else {
+        osml::knn_aggregate_kernel<double><<<grid, threads, 0, stream>>>(
+            static_cast<const double*>(nn_d), nn_i, q, ix->k, ix->label_bits.as<int64_t>(), ix->label_kind,
+            ix->n_labels, ix->gamma, ix->gamma_is_f32, ix->epsilon, task, d_out_pred);
+    }
+    ix->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return OSML_KNN_OK;
+}
+
+int check_predict_args(const osml_knn_index* ix, int64_t q) {
+    if (!ix) return fail(OSML_KNN_EINVAL, "null index");
+    if (q < 1) return fail(OSML_KNN_EINVAL, "no queries");
+    // np.argpartition(distances, k + 1) needs k + 1 < n; n_labels is the global row count
+    if (ix->n_labels < (int64_t)ix->k + 2) return fail(OSML_KNN_EINVAL, "fewer than k + 2 training rows");
+    return OSML_KNN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int osml_knn_abi_version(void) { return 1000; }
+
+const char* osml_knn_last_error(void) { return g_last_error.c_str(); }
+
+int osml_knn_create(osml_knn_index** out, int device, const void* train, int dtype, int layout, int64_t n, int64_t d,
+                    int sum_order, const void* labels, int label_dtype, int64_t n_labels, int64_t index_base, int k,
+                    double rbf_gamma, int gamma_is_f32, double epsilon) {
+    if (!out) return fail(OSML_KNN_EINVAL, "null out");
+    *out = nullptr;
+    if (!train || !labels) return fail(OSML_KNN_EINVAL, "null input");
+    if (k < 1) return fail(OSML_KNN_EINVAL, "k < 1");                       // predict.py:729-730
+    if (!(rbf_gamma > 0)) return fail(OSML_KNN_EINVAL, "rbf_gamma <= 0");   // predict.py:731-732
+    if (!(epsilon > 0)) return fail(OSML_KNN_EINVAL, "epsilon <= 0");       // model.py:11-12
+    if (n < 1 || d < 1) return fail(OSML_KNN_EINVAL, "empty train matrix"); // model.py:19-23
+    if (index_base < 0 || n_labels < index_base + n) return fail(OSML_KNN_EINVAL, "labels shorter than the shard");
+    if (n_labels < (int64_t)k + 1) return fail(OSML_KNN_EINVAL, "fewer than k + 1 training rows");  // predict.py:768
+    if (dtype_size(dtype) == 0) return fail(OSML_KNN_EUNSUPPORTED, "unsupported train dtype");
+    if (layout != OSML_KNN_ROW_MAJOR && layout != OSML_KNN_COL_MAJOR) return fail(OSML_KNN_EINVAL, "bad layout");
+    if (sum_order != OSML_KNN_SUM_PAIRWISE && sum_order != OSML_KNN_SUM_SEQUENTIAL)
+        return fail(OSML_KNN_EINVAL, "bad sum_order");
+    if (k + 1 > osml::kAggMaxK) return fail(OSML_KNN_EUNSUPPORTED, "k > 127 is not supported on the GPU path");
+    if (n >= 0x7fffffff || d >= (1 << 24)) return fail(OSML_KNN_EUNSUPPORTED, "shard too large (n < 2^31, d < 2^24)");
+
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(OSML_KNN_ECUDA, "no such CUDA device");
+    DeviceGuard guard(device);
+
+    osml_knn_index* ix = new (std::nothrow) osml_knn_index();
+    if (!ix) return fail(OSML_KNN_ENOMEM, "host allocation failed");
+    ix->device = device; ix->dtype = dtype; ix->n = n; ix->d = d; ix->sum_order = sum_order; ix->k = k;
+    ix->gamma = rbf_gamma; ix->gamma_is_f32 = gamma_is_f32 ? 1 : 0; ix->epsilon = epsilon;
+    ix->index_base = index_base; ix->n_labels = n_labels;
+
+    auto cleanup = [&](int rc) { osml_knn_destroy(ix); return rc; };
+    std::vector<int64_t> bits;
+    if (convert_labels(labels, label_dtype, n_labels, bits, &ix->label_kind))
+        return cleanup(fail(OSML_KNN_EUNSUPPORTED, "unsupported label dtype"));
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ix->ev0)) != cudaSuccess || (e = cudaEventCreate(&ix->ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&ix->ev2)) != cudaSuccess || (e = cudaEventCreate(&ix->ev3)) != cudaSuccess)
+        return cleanup(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
+    int rc = upload_matrix(ix, train, layout, n, d, ix->train, ix->stream);
+    if (rc != OSML_KNN_OK) return cleanup(rc);
+    if ((e = ix->label_bits.reserve((size_t)n_labels * 8)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(ix->label_bits.ptr, bits.data(), (size_t)n_labels * 8, cudaMemcpyHostToDevice,
+                             ix->stream)) != cudaSuccess)
+        return cleanup(fail(e == cudaErrorMemoryAllocation ? OSML_KNN_ENOMEM : OSML_KNN_ECUDA, cudaGetErrorString(e)));
+    if ((e = cudaStreamSynchronize(ix->stream)) != cudaSuccess) return cleanup(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
+    ix->stage.release();
+    *out = ix;
+    return OSML_KNN_OK;
+}
+
+int osml_knn_destroy(osml_knn_index* ix) {
+    if (!ix) return OSML_KNN_OK;
+    DeviceGuard guard(ix->device);
+    osml::tensor_release(ix->tensor);
+    ix->train.release(); ix->label_bits.release(); ix->stage.release(); ix->queries.release();
+    ix->part_d.release(); ix->part_i.release(); ix->nn_d.release(); ix->nn_i.release(); ix->pred.release();
+    if (ix->ev0) cudaEventDestroy(ix->ev0);
+    if (ix->ev1) cudaEventDestroy(ix->ev1);
+    if (ix->ev2) cudaEventDestroy(ix->ev2);
+    if (ix->ev3) cudaEventDestroy(ix->ev3);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+    return OSML_KNN_OK;
+}
+
+int osml_knn_neighbours_device(osml_knn_index* ix, const void* d_queries, int64_t q, int64_t* d_out_idx,
+                               void* d_out_dist, void* stream) {
+    if (!ix || !d_queries || !d_out_idx || !d_out_dist) return fail(OSML_KNN_EINVAL, "null argument");
+    DeviceGuard guard(ix->device);
+    return neighbours(ix, d_queries, q, d_out_dist, d_out_idx, static_cast<cudaStream_t>(stream));
+}
+
+int osml_knn_predict_device(osml_knn_index* ix, const void* d_queries, int64_t q, int task, double* d_out_pred,
+                            int64_t* d_out_idx, void* d_out_dist, void* stream_v) {
+    int rc = check_predict_args(ix, q);
+    if (rc != OSML_KNN_OK) return rc;
+    if (!d_queries || !d_out_pred) return fail(OSML_KNN_EINVAL, "null argument");
+    if (ix->n != ix->n_labels || ix->index_base != 0)
+        return fail(OSML_KNN_EINVAL, "index holds a shard: use neighbours + merge_predict");
+    DeviceGuard guard(ix->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const size_t ksel = (size_t)ix->ksel();
+    void* nn_d = d_out_dist;
+    int64_t* nn_i = d_out_idx;
+    if (!nn_d) { CUDA_TRY(ix->nn_d.reserve((size_t)q * ksel * ix->dist_size())); nn_d = ix->nn_d.ptr; }
+    if (!nn_i) { CUDA_TRY(ix->nn_i.reserve((size_t)q * ksel * 8)); nn_i = ix->nn_i.as<int64_t>(); }
+    CUDA_TRY(cudaEventRecord(ix->ev1, stream));
+    rc = neighbours(ix, d_queries, q, nn_d, nn_i, stream);
+    if (rc != OSML_KNN_OK) return rc;
+    CUDA_TRY(cudaEventRecord(ix->ev2, stream));
+    rc = aggregate(ix, nn_d, nn_i, q, task, d_out_pred, stream);
+    if (rc != OSML_KNN_OK) return rc;
+    ix->stats.queries += q;
+    return OSML_KNN_OK;
+}
+
+int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_t q, int task, double* out_pred,
+                     int64_t* out_idx, void* out_dist) {
+    int rc = check_predict_args(ix, q);
+    if (rc != OSML_KNN_OK) return rc;
+    if (!queries || !out_pred) return fail(OSML_KNN_EINVAL, "null argument");
+    if (layout != OSML_KNN_ROW_MAJOR && layout != OSML_KNN_COL_MAJOR) return fail(OSML_KNN_EINVAL, "bad layout");
+    DeviceGuard guard(ix->device);
+    const size_t ksel = (size_t)ix->ksel();
+    CUDA_TRY(cudaEventRecord(ix->ev0, ix->stream));
+    rc = upload_matrix(ix, queries, layout, q, ix->d, ix->queries, ix->stream);
+    if (rc != OSML_KNN_OK) return rc;
+    CUDA_TRY(ix->nn_d.reserve((size_t)q * ksel * ix->dist_size()));
+    CUDA_TRY(ix->nn_i.reserve((size_t)q * ksel * 8));
+    CUDA_TRY(ix->pred.reserve((size_t)q * 8));
+    rc = osml_knn_predict_device(ix, ix->queries.ptr, q, task, ix->pred.as<double>(), ix->nn_i.as<int64_t>(),
+                                 ix->nn_d.ptr, ix->stream);
+    if (rc != OSML_KNN_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_pred, ix->pred.ptr, (size_t)q * 8, cudaMemcpyDeviceToHost, ix->stream));
+    if (out_idx) CUDA_TRY(cudaMemcpyAsync(out_idx, ix->nn_i.ptr, (size_t)q * ksel * 8, cudaMemcpyDeviceToHost, ix->stream));
+    if (out_dist)
+        CUDA_TRY(cudaMemcpyAsync(out_dist, ix->nn_d.ptr, (size_t)q * ksel * ix->dist_size(), cudaMemcpyDeviceToHost,
+                                 ix->stream));
+    CUDA_TRY(cudaEventRecord(ix->ev3, ix->stream));
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ix->ev0, ix->ev3) == cudaSuccess) ix->stats.last_total_ms = ms;
+    if (cudaEventElapsedTime(&ms, ix->ev1, ix->ev2) == cudaSuccess) ix->stats.last_filter_ms = ms;
+    return OSML_KNN_OK;
+}
+
+int osml_knn_merge_predict_device(osml_knn_index* ix, const int64_t* d_part_idx, const void* d_part_dist, int parts,
+                                  int64_t q, int task, double* d_out_pred, int64_t* d_out_idx, void* d_out_dist,
+                                  void* stream_v) {
+    int rc = check_predict_args(ix, q);
+    if (rc != OSML_KNN_OK) return rc;
+    if (!d_part_idx || !d_part_dist || !d_out_pred) return fail(OSML_KNN_EINVAL, "null argument");
+    if (parts < 1 || parts > 64) return fail(OSML_KNN_EINVAL, "parts must be in 1..64");
+    DeviceGuard guard(ix->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int ksel = ix->ksel();
+    void* nn_d = d_out_dist;
+    int64_t* nn_i = d_out_idx;
+    if (!nn_d) { CUDA_TRY(ix->nn_d.reserve((size_t)q * ksel * ix->dist_size())); nn_d = ix->nn_d.ptr; }
+    if (!nn_i) { CUDA_TRY(ix->nn_i.reserve((size_t)q * ksel * 8)); nn_i = ix->nn_i.as<int64_t>(); }
+    const int threads = 128;
+    const unsigned grid = (unsigned)((q + threads - 1) / threads);
+    if (ix->dist_size() == 4)
+        osml::knn_merge_lists_kernel<float><<<grid, threads, 0, stream>>>(
+            static_cast<const float*>(d_part_dist), d_part_idx, parts, q * ksel, (int64_t)ksel, q, ksel,
+            static_cast<float*>(nn_d), nn_i);
+    else
+        osml::knn_merge_lists_kernel<double><<<grid, threads, 0, stream>>>(
+            static_cast<const double*>(d_part_dist), d_part_idx, parts, q * ksel, (int64_t)ksel, q, ksel,
+            static_cast<double*>(nn_d), nn_i);
+    ix->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    rc = aggregate(ix, nn_d, nn_i, q, task, d_out_pred, stream);
+    if (rc == OSML_KNN_OK) ix->stats.queries += q;
+    return rc;
+}
+
+int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
+    if (!ix || !name) return fail(OSML_KNN_EINVAL, "null argument");
+    const std::string key(name);
+    if (key == "path") {
+        const int v = (int)value;
+        if (v < OSML_KNN_PATH_AUTO || v > OSML_KNN_PATH_TENSOR) return fail(OSML_KNN_EINVAL, "bad path");
+        if (v == OSML_KNN_PATH_TENSOR && !osml::tensor_path_supported(ix->dtype, ix->n, ix->d, ix->k))
+            return fail(OSML_KNN_EUNSUPPORTED, "tensor path needs fp32 data, k + 1 + slack <= 64 and n >= 256");
+        ix->path = v;
+        return OSML_KNN_OK;
+    }
+    if (key == "slack") { ix->slack = (int)value; return OSML_KNN_OK; }
+    if (key == "query_block") { ix->query_block = (int64_t)value; return OSML_KNN_OK; }
+    return fail(OSML_KNN_EINVAL, "unknown option: " + key);
+}
+
+int osml_knn_get_stats(osml_knn_index* ix, osml_knn_stats* out) {
+    if (!ix || !out) return fail(OSML_KNN_EINVAL, "null argument");
+    ix->stats.device_bytes = (int64_t)(ix->train.cap + ix->label_bits.cap + ix->stage.cap + ix->queries.cap +
+                                       ix->part_d.cap + ix->part_i.cap + ix->nn_d.cap + ix->nn_i.cap + ix->pred.cap +
+                                       osml::tensor_bytes(ix->tensor));
+    *out = ix->stats;
+    return OSML_KNN_OK;
+}
+
+int osml_knn_reset_stats(osml_knn_index* ix) {
+    if (!ix) return fail(OSML_KNN_EINVAL, "null argument");
+    ix->stats = osml_knn_stats{};
+    return OSML_KNN_OK;
+}
+
+int osml_knn_describe(osml_knn_index* ix, int64_t* n, int64_t* d, int* k, int* dtype, int* dist_elem_size) {
+    if (!ix) return fail(OSML_KNN_EINVAL, "null argument");
+    if (n) *n = ix->n;
+    if (d) *d = ix->d;
+    if (k) *k = ix->k;
+    if (dtype) *dtype = ix->dtype;
+    if (dist_elem_size) *dist_elem_size = (int)ix->dist_size();
+    return OSML_KNN_OK;
+}
+
+}  // extern "C"
