@@ -1,15 +1,481 @@
-// K0 / K1 / K3: tcgen05 tensor-core candidate filter with exact rescoring (interface; kernels in knn_tensor_impl.cuh).
+// K0 / K1 / K3: tcgen05 tensor-core candidate filter with a provably complete exact rescoring.
+//
+// The reference computes sqrt(sum((t - q)^2)) for every (query, train row) pair in fp32 (predict.py:742) and keeps the
+// k+1 smallest (predict.py:750).  Doing that arithmetic literally costs 3 un-fusable CUDA-core instructions per
+// element (K2).  Here the tensor cores only *filter*:
+//
+//   K0  knn_prep_rows      one streaming pass: centre by the train column means, round to bf16, append three bf16
+//                          columns holding -0.5*|t^|^2 (hi/mid/lo split, exact to 2^-24) to each train row and
+//                          (1, 1, 1) to each query row, record |q^|^2 and the rounding residuals |q^ - (q - c)|.
+//   K1  knn_tc_filter      persistent tcgen05 kernel: acc[q][t] = q^ . t^ - 0.5*|t^|^2 (so |q^ - t^|^2 = |q^|^2 - 2*acc)
+//                          with TMA-staged, 128B-swizzled operand tiles and FP32 accumulators in TMEM; the epilogue
+//                          reads each 128 x 256 accumulator tile straight out of TMEM and keeps, per query, the K'
+//                          largest acc per train segment.  The distance matrix never leaves the SM.
+//   K3  knn_rescore        per query: exact distances of the candidates in the oracle's arithmetic and summation
+//                          order, top-(k+1) by (distance, index), and a completeness proof -- every row the filter
+//                          dropped has acc <= the segment's K'-th best, which bounds its true distance from below
+//                          by sqrt(|q^|^2 - 2*(thr + eps)) - (Eq + Et); if that bound exceeds the exact (k+1)-th
+//                          distance the result equals the brute-force one.  Queries that cannot be proven are
+//                          re-run on K2.  So the output is bit-identical to K2 / the oracle whatever the filter does.
 #pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
+#include <cmath>
 #include <functional>
 #include <string>
+#include <vector>
+
+#include "knn_common.cuh"
+#include "knn_ptx.cuh"
 
 namespace osml {
 
+// ---------------------------------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kTcBM = 128;            // queries per tile (UMMA M)
+constexpr int kTcBN = 256;            // train rows per tile (UMMA N)
+constexpr int kTcKB = 64;             // bf16 per K block = one 128-byte swizzled row
+constexpr int kTcABlockBytes = kTcBM * 128;   // 16 KB
+constexpr int kTcBStageBytes = kTcBN * 128;   // 32 KB
+constexpr int kTcThreads = 384;       // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int kTcMaxKPrime = 64;
+constexpr int kTcMaxCand = 512;       // candidates per query K3 handles (slots * K')
+constexpr float kTcPadScore = -3.0e38f;
+
+struct TcParams {
+    int nkb;             // K blocks of the padded feature dimension
+    int ksteps;          // UMMA K steps (16 bf16 each) actually needed: ceil((d + 3) / 16)
+    int nqt;             // query tiles
+    int nseg;            // train segments
+    int tiles_per_seg;   // 256-row tiles per segment
+    int tiles_total;
+    int kprime;          // candidates kept per (query, slot)
+    int epi_warps;       // 4 or 8
+    int stages;          // B ring depth
+    int nslot;           // nseg * halves
+    float* cand_val;     // [qpad][nslot][kprime]
+    int* cand_idx;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K0: preparation
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void tc_col_partial_sums_kernel(const float* __restrict__ x, int64_t n, int d, int rows_per_block,
+                                           double* __restrict__ partial) {
+    __shared__ double red[8][33];
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(n, r0 + rows_per_block);
+    for (int j0 = 0; j0 < d; j0 += 32) {
+        const int j = j0 + threadIdx.x;
+        double s = 0.0;
+        if (j < d)
+            for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += (double)x[r * d + j];
+        red[threadIdx.y][threadIdx.x] = s;
+        __syncthreads();
+        if (threadIdx.y == 0 && j < d) {
+            double t = 0.0;
+            for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+            partial[(int64_t)blockIdx.x * d + j] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void tc_col_mean_kernel(const double* __restrict__ partial, int nblocks, int d, int64_t n,
+                                   float* __restrict__ center) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * d + j];
+    const float c = (float)(s / (double)n);
+    center[j] = (c == c && fabsf(c) < INFINITY) ? c : 0.0f;
+}
+
+struct TcPrepStats {          // device-side reductions over the train rows
+    unsigned long long et_max_bits;      // max |t^ - (t - c)|     (double bits; non-negative doubles order like uint64)
+    unsigned long long tnorm_max_bits;   // max |t^|
+    int nonfinite;
+};
+
+// one warp per row
+template <bool kTrain>
+__global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t npad, int d, int dp,
+                                    const float* __restrict__ center, __nv_bfloat16* __restrict__ out,
+                                    double* __restrict__ norm2, double* __restrict__ err, TcPrepStats* stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= npad) return;
+    __nv_bfloat16* o = out + row * dp;
+    if (row >= n) {                       // padding row: can never be selected (train) / is ignored (queries)
+        for (int j = lane; j < dp; j += 32) o[j] = __float2bfloat16(0.0f);
+        if (kTrain && lane == 0) o[d] = __float2bfloat16(kTcPadScore);
+        if (!kTrain && lane == 0 && norm2) { norm2[row] = 0.0; err[row] = 0.0; }
+        return;
+    }
+    const float* xr = x + row * d;
+    double n2 = 0.0, e2 = 0.0;
+    for (int j = lane; j < d; j += 32) {
+        const float v = xr[j], c = center[j];
+        const __nv_bfloat16 h = __float2bfloat16_rn(__fsub_rn(v, c));
+        o[j] = h;
+        const double hd = (double)__bfloat162float(h);
+        const double diff = hd - ((double)v - (double)c);
+        n2 += hd * hd;
+        e2 += diff * diff;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+        e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+    }
+    for (int j = d + 3 + lane; j < dp; j += 32) o[j] = __float2bfloat16(0.0f);
+    if (lane == 0) {
+        const double e = sqrt(e2) * (1.0 + 1e-12);
+        if (kTrain) {
+            const double h = -0.5 * n2;
+            const __nv_bfloat16 h1 = __double2bfloat16(h);
+            const double r1 = h - (double)__bfloat162float(h1);
+            const __nv_bfloat16 h2 = __double2bfloat16(r1);
+            const double r2 = r1 - (double)__bfloat162float(h2);
+            const __nv_bfloat16 h3 = __double2bfloat16(r2);
+            o[d] = h1; o[d + 1] = h2; o[d + 2] = h3;
+            const double tn = sqrt(n2) * (1.0 + 1e-12);
+            if (!(n2 < 1.0e37) || !(e2 < 1.0e37)) atomicExch(&stats->nonfinite, 1);
+            else {
+                atomicMax(&stats->et_max_bits, (unsigned long long)__double_as_longlong(e));
+                atomicMax(&stats->tnorm_max_bits, (unsigned long long)__double_as_longlong(tn));
+            }
+        } else {
+            o[d] = __float2bfloat16(1.0f); o[d + 1] = __float2bfloat16(1.0f); o[d + 2] = __float2bfloat16(1.0f);
+            norm2[row] = n2;
+            err[row] = e;     // NaN / inf propagate and make the query fall back
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1: persistent tcgen05 filter
+// ---------------------------------------------------------------------------------------------------------------------
+struct TcList {
+    float* val; int* idx; int kprime; int stride;     // slot e of this thread at val[e * stride]
+    float thr; int pos_min;
+    __device__ __forceinline__ void reset() {
+        for (int e = 0; e < kprime; ++e) { val[e * stride] = -INFINITY; idx[e * stride] = -1; }
+        thr = -INFINITY; pos_min = 0;
+    }
+    // precondition v > thr: replaces the current minimum and finds the new one
+    __device__ __noinline__ void insert(float v, int row) {
+        val[pos_min * stride] = v; idx[pos_min * stride] = row;
+        float m = val[0]; int pm = 0;
+        for (int e = 1; e < kprime; ++e) {
+            const float x = val[e * stride];
+            if (x < m) { m = x; pm = e; }
+        }
+        thr = m; pos_min = pm;
+    }
+};
+
+__device__ __forceinline__ float tc_max32(const float (&v)[32]) {
+    float a0 = ptx::fmax3(v[0], v[1], v[2]), a1 = ptx::fmax3(v[3], v[4], v[5]), a2 = ptx::fmax3(v[6], v[7], v[8]);
+    float a3 = ptx::fmax3(v[9], v[10], v[11]), a4 = ptx::fmax3(v[12], v[13], v[14]), a5 = ptx::fmax3(v[15], v[16], v[17]);
+    float a6 = ptx::fmax3(v[18], v[19], v[20]), a7 = ptx::fmax3(v[21], v[22], v[23]), a8 = ptx::fmax3(v[24], v[25], v[26]);
+    float a9 = ptx::fmax3(v[27], v[28], v[29]);
+    float b0 = ptx::fmax3(a0, a1, a2), b1 = ptx::fmax3(a3, a4, a5), b2 = ptx::fmax3(a6, a7, a8);
+    float b3 = ptx::fmax3(a9, v[30], v[31]);
+    return fmaxf(ptx::fmax3(b0, b1, b2), b3);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // carve: [A blocks][B ring][lists][barriers]
+    unsigned char* a_smem = smem;
+    unsigned char* b_smem = a_smem + (size_t)p.nkb * kTcABlockBytes;
+    const int epi_threads = p.epi_warps * 32;
+    float* list_val = reinterpret_cast<float*>(b_smem + (size_t)p.stages * kTcBStageBytes);
+    int* list_idx = reinterpret_cast<int*>(list_val + (size_t)p.kprime * epi_threads);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(list_idx + (size_t)p.kprime * epi_threads);
+    uint64_t* full_bar = bars;                    // [stages]
+    uint64_t* empty_bar = bars + 8;               // [stages]
+    uint64_t* tmem_full = bars + 16;              // [2]
+    uint64_t* tmem_empty = bars + 18;             // [2]
+    uint64_t* a_full = bars + 20;
+    uint64_t* a_empty = bars + 21;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nitems = p.nqt * p.nseg;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], epi_threads); }
+        ptx::mbar_init(a_full, 1);
+        ptx::mbar_init(a_empty, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+                const int seg = item / p.nqt, qt = item % p.nqt;
+                const int tile0 = seg * p.tiles_per_seg;
+                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+                ptx::mbar_wait(a_empty, (it & 1) ^ 1);
+                ptx::mbar_expect_tx(a_full, (uint32_t)p.nkb * kTcABlockBytes);
+                for (int kb = 0; kb < p.nkb; ++kb)
+                    ptx::tma_load_2d(a_smem + (size_t)kb * kTcABlockBytes, &map_a, a_full, kb * kTcKB, qt * kTcBM);
+                for (int t = 0; t < ntiles; ++t) {
+                    const int row0 = (tile0 + t) * kTcBN;
+                    for (int kb = 0; kb < p.nkb; ++kb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ptx::mbar_expect_tx(&full_bar[stage], kTcBStageBytes);
+                        ptx::tma_load_2d(b_smem + (size_t)stage * kTcBStageBytes, &map_b, &full_bar[stage], kb * kTcKB,
+                                         row0);
+                        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = ptx::umma_idesc_bf16(kTcBM, kTcBN);
+            const uint32_t a_addr = ptx::smem_u32(a_smem), b_addr = ptx::smem_u32(b_smem);
+            uint32_t stage = 0, phase = 0, it = 0, acc_it = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+                const int seg = item / p.nqt;
+                const int tile0 = seg * p.tiles_per_seg;
+                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+                ptx::mbar_wait(a_full, it & 1);
+                ptx::tc_fence_after();
+                for (int t = 0; t < ntiles; ++t, ++acc_it) {
+                    const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                    ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * kTcBN;
+                    for (int kb = 0; kb < p.nkb; ++kb) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after();
+                        const int nks = min(4, p.ksteps - kb * 4);
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint64_t da = ptx::umma_desc_k_sw128(a_addr + kb * kTcABlockBytes + ks * 32);
+                            const uint64_t db = ptx::umma_desc_k_sw128(b_addr + stage * kTcBStageBytes + ks * 32);
+                            ptx::umma_bf16_ss(tmem_d, da, db, idesc, (uint32_t)((kb | ks) != 0));
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);       // frees the smem stage when these MMAs retire
+                        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                    }
+                    ptx::umma_commit(&tmem_full[as]);              // accumulator tile ready for the epilogue
+                }
+                ptx::umma_commit(a_empty);                         // query tile may be overwritten
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + p.epi_warps) {
+        // ===== epilogue: TMEM -> registers -> per-query running top-K' =====
+        const int ew = warp - 4;
+        const int quarter = ew & 3;                     // == warp % 4: the TMEM lane quarter this warp may read
+        const int half = ew >> 2;                       // column half when 8 warps share the tile
+        const int halves = p.epi_warps >> 2;
+        const int cols = kTcBN / halves;                // columns of each tile this thread scans
+        const int et = ew * 32 + lane;                  // epilogue thread id
+        const int m = quarter * 32 + lane;              // query row inside the tile == TMEM lane
+        TcList list;
+        list.val = list_val + et; list.idx = list_idx + et; list.kprime = p.kprime; list.stride = epi_threads;
+        uint32_t acc_it = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int seg = item / p.nqt, qt = item % p.nqt;
+            const int tile0 = seg * p.tiles_per_seg;
+            const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+            list.reset();
+            for (int t = 0; t < ntiles; ++t, ++acc_it) {
+                const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
+                const int row_base = (tile0 + t) * kTcBN + half * cols;
+                for (int c = 0; c < cols; c += 32) {
+                    float v[32];
+                    ptx::tmem_ld_32x32(taddr + c, v);
+                    ptx::tmem_ld_wait();
+                    const float mx = tc_max32(v);
+                    if (mx > list.thr) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (v[i] > list.thr) list.insert(v[i], row_base + c + i);
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tmem_empty[as]);
+            }
+            // publish this (query, slot) list
+            const size_t q = (size_t)qt * kTcBM + m;
+            const size_t slot = (size_t)seg * halves + half;
+            float* ov = p.cand_val + (q * p.nslot + slot) * p.kprime;
+            int* oi = p.cand_idx + (q * p.nslot + slot) * p.kprime;
+            for (int e = 0; e < p.kprime; ++e) { ov[e] = list.val[e * list.stride]; oi[e] = list.idx[e * list.stride]; }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K3: exact rescoring + completeness proof, one warp per query
+// ---------------------------------------------------------------------------------------------------------------------
+struct TcBounds {
+    double et_max;        // max over train rows of |t^ - (t - c)|
+    double tnorm_max;     // max |t^|
+    double c_mma;         // relative accumulation error of the tensor core sum, per unit of sum |terms|
+    double gamma;         // relative error of the oracle's fp32 distance
+};
+
+constexpr int kRescoreWarps = 4;
+
+__global__ void __launch_bounds__(32 * kRescoreWarps)
+knn_rescore_kernel(const float* __restrict__ train, const float* __restrict__ queries, int d, int sum_order,
+                   int64_t q_count, int ksel, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
+                   int nslot, int kprime, const double* __restrict__ qnorm2, const double* __restrict__ qerr,
+                   TcBounds bounds, int64_t index_base, float* __restrict__ out_d, int64_t* __restrict__ out_i,
+                   int* __restrict__ flags) {
+    __shared__ float s_dist[kRescoreWarps][kTcMaxCand];
+    __shared__ int s_idx[kRescoreWarps][kTcMaxCand];
+    __shared__ float s_best[kRescoreWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * kRescoreWarps + warp;
+    if (q >= q_count) return;
+    const int ncand = nslot * kprime;
+    const float* cv = cand_val + (size_t)q * ncand;
+    const int* ci = cand_idx + (size_t)q * ncand;
+    const float* qrow = queries + (size_t)q * d;
+    float* dist = s_dist[warp];
+    int* idx = s_idx[warp];
+
+    for (int c = lane; c < ncand; c += 32) {
+        const int row = ci[c];
+        if (row >= 0) {
+            dist[c] = exact_distance<float>(train + (size_t)row * d, qrow, d, sum_order);
+            idx[c] = row;
+        } else {
+            dist[c] = nan_of<float>();
+            idx[c] = kIdxSentinel;
+        }
+    }
+    __syncwarp();
+    // rank by (distance, index); keys are unique because the slots cover disjoint row ranges
+    int nvalid_local = 0;
+    for (int c = lane; c < ncand; c += 32) {
+        const int ic = idx[c];
+        if (ic == kIdxSentinel) continue;
+        ++nvalid_local;
+        const float dc = dist[c];
+        int rank = 0;
+        for (int o = 0; o < ncand; ++o) rank += key_less(dist[o], idx[o], dc, ic) ? 1 : 0;
+        if (rank < ksel) {
+            out_d[q * ksel + rank] = dc;
+            out_i[q * ksel + rank] = index_base + ic;
+            if (rank == ksel - 1) s_best[warp] = dc;
+        }
+    }
+    int nvalid = nvalid_local;
+    for (int off = 16; off > 0; off >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, off);
+    __syncwarp();
+    bool ok = nvalid >= ksel;
+    if (ok) {
+        const double dk = (double)s_best[warp] * (1.0 + 9.5367431640625e-07);   // (k+1)-th exact distance, 2^-20 margin
+        const double n2 = qnorm2[q], eq = qerr[q];
+        const double qn = sqrt(n2);
+        const double eps = bounds.c_mma * (qn * bounds.tnorm_max + 0.5 * bounds.tnorm_max * bounds.tnorm_max);
+        for (int s = lane; s < nslot; s += 32) {
+            float thr = INFINITY;
+            bool full = true;
+            for (int e = 0; e < kprime; ++e) {
+                if (ci[s * kprime + e] < 0) full = false;
+                thr = fminf(thr, cv[s * kprime + e]);
+            }
+            if (!full) continue;              // fewer than K' real rows in this slot: nothing was dropped
+            const double l2 = n2 - 2.0 * ((double)thr + eps);
+            const double lower = (sqrt(fmax(l2, 0.0)) - (eq + bounds.et_max)) * (1.0 - bounds.gamma);
+            if (!(lower > dk)) ok = false;    // also catches NaN
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) flags[q] = ok ? 0 : 1;
+}
+
+// ---- fallback plumbing ------------------------------------------------------------------------------------------------
+__global__ void tc_compact_flags_kernel(const int* __restrict__ flags, int64_t q_count, int* __restrict__ list,
+                                        int* __restrict__ count) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < q_count && flags[q]) list[atomicAdd(count, 1)] = (int)q;
+}
+
+__global__ void tc_gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ list, int count, int d,
+                                      float* __restrict__ dst) {
+    const int r = blockIdx.x;
+    if (r >= count) return;
+    const float* s = src + (size_t)list[r] * d;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) dst[(size_t)r * d + j] = s[j];
+}
+
+__global__ void tc_scatter_lists_kernel(const float* __restrict__ src_d, const int64_t* __restrict__ src_i,
+                                        const int* __restrict__ list, int count, int ksel, float* __restrict__ dst_d,
+                                        int64_t* __restrict__ dst_i) {
+    const int r = blockIdx.x;
+    if (r >= count) return;
+    const size_t q = (size_t)list[r];
+    for (int e = threadIdx.x; e < ksel; e += blockDim.x) {
+        dst_d[q * ksel + e] = src_d[(size_t)r * ksel + e];
+        dst_i[q * ksel + e] = src_i[(size_t)r * ksel + e];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+struct TcBuffer {
+    void* ptr = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
 struct TensorState {
     bool ready = false;
-    size_t bytes = 0;
+    bool usable = false;          // false if the train set has non-finite rows (then only K2 is exact)
+    int64_t npad = 0; int dp = 0;
+    double et_max = 0.0, tnorm_max = 0.0;
+    TcBuffer train_bf16, center, stats, partial;
+    TcBuffer q_bf16, q_norm2, q_err, cand_val, cand_idx, flags, fb_list, fb_count, fb_queries, fb_d, fb_i;
+    CUtensorMap map_b;
+    void* encode_fn = nullptr;
+    int sm_count = 0;
+    int smem_optin = 0;
 };
 
 struct TensorLaunch {
@@ -18,13 +484,232 @@ struct TensorLaunch {
 
 using DirectFallback = std::function<int(const void*, int64_t, void*, int64_t*)>;
 
-inline bool tensor_path_supported(int, int64_t, int64_t, int) { return false; }
-inline size_t tensor_bytes(const TensorState& s) { return s.bytes; }
-inline void tensor_release(TensorState&) {}
-inline int tensor_neighbours(TensorState&, const TensorLaunch&, const void*, int64_t, void*, int64_t*, cudaStream_t,
-                             int64_t*, int64_t*, std::string* err, const DirectFallback&) {
-    if (err) *err = "tensor path not built";
-    return 4;
+inline int tc_default_slack(int k) { return std::max(5, (k + 1) / 3); }
+
+inline int tc_kprime(int k, int slack) {
+    if (slack < 0) slack = tc_default_slack(k);
+    int kp = k + 1 + slack;
+    return (kp + 7) / 8 * 8;
+}
+
+inline bool tensor_path_supported(int dtype, int64_t n, int64_t d, int k) {
+    if (dtype != 0 /* OSML_KNN_F32 */) return false;
+    if (n < 256 || d < 1) return false;
+    const int64_t dp = (d + 3 + kTcKB - 1) / kTcKB * kTcKB;
+    if (dp / kTcKB > 5) return false;             // query tile must stay resident in shared memory (d <= 317)
+    return tc_kprime(k, -1) <= kTcMaxKPrime;
+}
+
+inline size_t tensor_bytes(const TensorState& s) {
+    return s.train_bf16.cap + s.center.cap + s.stats.cap + s.partial.cap + s.q_bf16.cap + s.q_norm2.cap + s.q_err.cap +
+           s.cand_val.cap + s.cand_idx.cap + s.flags.cap + s.fb_list.cap + s.fb_count.cap + s.fb_queries.cap +
+           s.fb_d.cap + s.fb_i.cap;
+}
+
+inline void tensor_release(TensorState& s) {
+    for (TcBuffer* b : {&s.train_bf16, &s.center, &s.stats, &s.partial, &s.q_bf16, &s.q_norm2, &s.q_err, &s.cand_val,
+                        &s.cand_idx, &s.flags, &s.fb_list, &s.fb_count, &s.fb_queries, &s.fb_d, &s.fb_i})
+        b->release();
+    s.ready = false;
+}
+
+typedef CUresult (*TcEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline int tc_make_map(TensorState& st, CUtensorMap* map, void* base, int64_t rows, int dp, int box_rows,
+                       std::string* err) {
+    const cuuint64_t dims[2] = {(cuuint64_t)dp, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)dp * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcKB, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<TcEncodeTiledFn>(st.encode_fn)(
+        map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return 2;
+    }
+    return 0;
+}
+
+#define TC_TRY(expr)                                                                           \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            cudaGetLastError();                                                                \
+            if (err) *err = std::string(#expr) + ": " + cudaGetErrorString(e__);               \
+            return e__ == cudaErrorMemoryAllocation ? 3 : 2;                                   \
+        }                                                                                      \
+    } while (0)
+
+// one-time K0 over the train set
+inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stream, int64_t* launches,
+                      std::string* err) {
+    if (st.ready) return 0;
+    int dev = 0;
+    TC_TRY(cudaGetDevice(&dev));
+    TC_TRY(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    TC_TRY(cudaDeviceGetAttribute(&st.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cudaDriverEntryPointQueryResult qres;
+    TC_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &st.encode_fn, cudaEnableDefault, &qres));
+    if (!st.encode_fn || qres != cudaDriverEntryPointSuccess) {
+        if (err) *err = "cuTensorMapEncodeTiled is not available from the driver";
+        return 2;
+    }
+    const int d = (int)tl.d;
+    st.dp = (d + 3 + kTcKB - 1) / kTcKB * kTcKB;
+    st.npad = (tl.n + kTcBN - 1) / kTcBN * kTcBN;
+    const float* train = static_cast<const float*>(tl.train);
+    const int rows_per_block = 2048;
+    const int nblocks = (int)((tl.n + rows_per_block - 1) / rows_per_block);
+    TC_TRY(st.partial.reserve((size_t)nblocks * d * sizeof(double)));
+    TC_TRY(st.center.reserve((size_t)d * sizeof(float)));
+    TC_TRY(st.stats.reserve(sizeof(TcPrepStats)));
+    TC_TRY(st.train_bf16.reserve((size_t)st.npad * st.dp * sizeof(__nv_bfloat16)));
+    TC_TRY(cudaMemsetAsync(st.stats.ptr, 0, sizeof(TcPrepStats), stream));
+    tc_col_partial_sums_kernel<<<nblocks, dim3(32, 8), 0, stream>>>(train, tl.n, d, rows_per_block,
+                                                                    st.partial.as<double>());
+    tc_col_mean_kernel<<<(d + 127) / 128, 128, 0, stream>>>(st.partial.as<double>(), nblocks, d, tl.n,
+                                                            st.center.as<float>());
+    const int64_t threads = st.npad * 32;
+    tc_prep_rows_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+        train, tl.n, st.npad, d, st.dp, st.center.as<float>(), st.train_bf16.as<__nv_bfloat16>(), nullptr, nullptr,
+        st.stats.as<TcPrepStats>());
+    *launches += 3;
+    TC_TRY(cudaGetLastError());
+    TcPrepStats hs;
+    TC_TRY(cudaMemcpyAsync(&hs, st.stats.ptr, sizeof(hs), cudaMemcpyDeviceToHost, stream));
+    TC_TRY(cudaStreamSynchronize(stream));
+    st.partial.release();
+    double et, tn;
+    static_assert(sizeof(double) == sizeof(unsigned long long), "double bits");
+    memcpy(&et, &hs.et_max_bits, 8);
+    memcpy(&tn, &hs.tnorm_max_bits, 8);
+    st.et_max = et; st.tnorm_max = tn;
+    st.usable = hs.nonfinite == 0;
+    if (st.usable) {
+        int rc = tc_make_map(st, &st.map_b, st.train_bf16.ptr, st.npad, st.dp, kTcBN, err);
+        if (rc) return rc;
+    }
+    st.ready = true;
+    return 0;
+}
+
+// neighbour search for one block of queries (device, row-major fp32).  out_d/out_i: [q][k+1] final lists.
+inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
+                               float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
+                               int64_t* launches, std::string* err, const DirectFallback& direct) {
+    const int d = (int)tl.d;
+    const int ksel = tl.k + 1;
+    const int kprime = tc_kprime(tl.k, tl.slack);
+    if (kprime > kTcMaxKPrime) { if (err) *err = "k + 1 + slack exceeds 64"; return 4; }
+    const int epi_warps = kprime <= 24 ? 8 : 4;
+    const int halves = epi_warps / 4;
+    const int64_t qpad = (q + kTcBM - 1) / kTcBM * kTcBM;
+    const int nqt = (int)(qpad / kTcBM);
+    const int tiles_total = (int)(st.npad / kTcBN);
+    const int nkb = st.dp / kTcKB;
+    const int ksteps = (d + 3 + 15) / 16;
+
+    // segments: enough (query tile, segment) items to balance the persistent grid, few enough to keep K3 cheap
+    int max_seg_by_cand = std::max(1, kTcMaxCand / (kprime * halves));
+    int nseg = (3 * st.sm_count + nqt - 1) / nqt;
+    nseg = std::max(1, std::min(nseg, std::min(max_seg_by_cand, std::max(1, tiles_total / 8))));
+    int tiles_per_seg = (tiles_total + nseg - 1) / nseg;
+    nseg = (tiles_total + tiles_per_seg - 1) / tiles_per_seg;
+    const int nslot = nseg * halves;
+
+    const size_t list_bytes = (size_t)kprime * epi_warps * 32 * 8;
+    const size_t fixed = (size_t)nkb * kTcABlockBytes + list_bytes + 256 + 1024;
+    int stages = (int)(((size_t)st.smem_optin - fixed) / kTcBStageBytes);
+    stages = std::min(stages, 6);
+    if (stages < 2) { if (err) *err = "not enough shared memory for the tensor filter"; return 4; }
+    const size_t smem = (size_t)nkb * kTcABlockBytes + (size_t)stages * kTcBStageBytes + list_bytes + 256;
+
+    TC_TRY(st.q_bf16.reserve((size_t)qpad * st.dp * sizeof(__nv_bfloat16)));
+    TC_TRY(st.q_norm2.reserve((size_t)qpad * sizeof(double)));
+    TC_TRY(st.q_err.reserve((size_t)qpad * sizeof(double)));
+    TC_TRY(st.cand_val.reserve((size_t)qpad * nslot * kprime * sizeof(float)));
+    TC_TRY(st.cand_idx.reserve((size_t)qpad * nslot * kprime * sizeof(int)));
+    TC_TRY(st.flags.reserve((size_t)q * sizeof(int)));
+    TC_TRY(st.fb_list.reserve((size_t)q * sizeof(int)));
+    TC_TRY(st.fb_count.reserve(sizeof(int)));
+
+    const int64_t threads = qpad * 32;
+    tc_prep_rows_kernel<false><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+        d_queries, q, qpad, d, st.dp, st.center.as<float>(), st.q_bf16.as<__nv_bfloat16>(), st.q_norm2.as<double>(),
+        st.q_err.as<double>(), nullptr);
+    ++*launches;
+    TC_TRY(cudaGetLastError());
+
+    CUtensorMap map_a;
+    int rc = tc_make_map(st, &map_a, st.q_bf16.ptr, qpad, st.dp, kTcBM, err);
+    if (rc) return rc;
+
+    TcParams p;
+    p.nkb = nkb; p.ksteps = ksteps; p.nqt = nqt; p.nseg = nseg; p.tiles_per_seg = tiles_per_seg;
+    p.tiles_total = tiles_total; p.kprime = kprime; p.epi_warps = epi_warps; p.stages = stages; p.nslot = nslot;
+    p.cand_val = st.cand_val.as<float>(); p.cand_idx = st.cand_idx.as<int>();
+    TC_TRY(cudaFuncSetAttribute(knn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(nqt * nseg, st.sm_count);
+    knn_tc_filter_kernel<<<grid, kTcThreads, smem, stream>>>(map_a, st.map_b, p);
+    ++*launches;
+    TC_TRY(cudaGetLastError());
+
+    TcBounds b;
+    b.et_max = st.et_max; b.tnorm_max = st.tnorm_max;
+    b.c_mma = (double)(ksteps * 16 + 8) * 2.384185791015625e-07 + 1.2e-7;   // (K + 8) * 2^-22  + norm split 2^-23
+    b.gamma = (double)(d + 4) * 1.1920928955078125e-07;                      // (D + 4) * 2^-23
+    TC_TRY(cudaMemsetAsync(st.fb_count.ptr, 0, sizeof(int), stream));
+    knn_rescore_kernel<<<(unsigned)((q + kRescoreWarps - 1) / kRescoreWarps), 32 * kRescoreWarps, 0, stream>>>(
+        static_cast<const float*>(tl.train), d_queries, d, tl.sum_order, q, ksel, st.cand_val.as<float>(),
+        st.cand_idx.as<int>(), nslot, kprime, st.q_norm2.as<double>(), st.q_err.as<double>(), b, tl.index_base, out_d,
+        out_i, st.flags.as<int>());
+    tc_compact_flags_kernel<<<(unsigned)((q + 255) / 256), 256, 0, stream>>>(st.flags.as<int>(), q, st.fb_list.as<int>(),
+                                                                             st.fb_count.as<int>());
+    *launches += 2;
+    TC_TRY(cudaGetLastError());
+    int count = 0;
+    TC_TRY(cudaMemcpyAsync(&count, st.fb_count.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    TC_TRY(cudaStreamSynchronize(stream));
+    if (count > 0) {
+        TC_TRY(st.fb_queries.reserve((size_t)count * d * sizeof(float)));
+        TC_TRY(st.fb_d.reserve((size_t)count * ksel * sizeof(float)));
+        TC_TRY(st.fb_i.reserve((size_t)count * ksel * sizeof(int64_t)));
+        tc_gather_rows_kernel<<<count, 128, 0, stream>>>(d_queries, st.fb_list.as<int>(), count, d,
+                                                         st.fb_queries.as<float>());
+        ++*launches;
+        rc = direct(st.fb_queries.ptr, count, st.fb_d.ptr, st.fb_i.as<int64_t>());
+        if (rc) return rc;
+        tc_scatter_lists_kernel<<<count, 64, 0, stream>>>(st.fb_d.as<float>(), st.fb_i.as<int64_t>(),
+                                                          st.fb_list.as<int>(), count, ksel, out_d, out_i);
+        ++*launches;
+        TC_TRY(cudaGetLastError());
+        *fallback += count;
+    }
+    return 0;
+}
+
+inline int tensor_neighbours(TensorState& st, const TensorLaunch& tl, const void* d_queries, int64_t q, void* out_d,
+                             int64_t* out_i, cudaStream_t stream, int64_t* fallback, int64_t* launches,
+                             std::string* err, const DirectFallback& direct) {
+    int rc = tc_prepare(st, tl, stream, launches, err);
+    if (rc) return rc;
+    if (!st.usable) {                       // non-finite train rows: the filter's bounds do not hold
+        *fallback += q;
+        return direct(d_queries, q, out_d, out_i);
+    }
+    const int64_t block = 131072;
+    const int ksel = tl.k + 1;
+    for (int64_t q0 = 0; q0 < q; q0 += block) {
+        const int64_t qb = std::min(block, q - q0);
+        rc = tc_neighbours_block(st, tl, static_cast<const float*>(d_queries) + q0 * tl.d, qb,
+                                 static_cast<float*>(out_d) + q0 * ksel, out_i + q0 * ksel, stream, fallback, launches,
+                                 err, direct);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // namespace osml

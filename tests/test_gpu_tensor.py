@@ -1,0 +1,105 @@
+"""GPU parity of the tcgen05 filter path (K0 + K1 + K3, with K2 for unproven queries) against the oracle.
+
+The path is exact by construction (completeness proof or fallback), so besides bit-parity these tests assert that the
+filter actually carries the load: the share of queries that had to be re-run on the direct kernel must stay small."""
+import numpy as np
+import pytest
+
+from osml_b200 import _native
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(train, labels, test, k, task='classification', gamma=1, slack=None):
+    ix = _native.Index(train, labels, k, gamma, 1e-8)
+    ix.set_option('path', _native.PATH_TENSOR)
+    if slack is not None:
+        ix.set_option('slack', slack)
+    code = _native.REGRESSION if task == 'regression' else _native.CLASSIFICATION
+    pred, idx, dist = ix.predict(test, code, return_neighbours=True)
+    stats = ix.stats()
+    ix.close()
+    return pred, idx, dist, stats
+
+
+@pytest.mark.parametrize('n,d,q,k', [
+    (20000, 128, 1000, 10),      # config-4 shape, scaled down
+    (5000, 96, 300, 32),         # config-5 feature width and k
+    (777, 1, 130, 3), (3001, 3, 257, 7), (4096, 17, 128, 1), (10000, 61, 64, 10), (10000, 62, 64, 10),
+    (2500, 200, 100, 5), (3000, 317, 50, 10),
+])
+def test_gaussian_matches_oracle_bit_for_bit(n, d, q, k):
+    rng = np.random.default_rng(n + d)
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = rng.standard_normal((q, d), dtype=np.float32)
+    labels = rng.integers(0, 10, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+    assert stats['tensor_queries'] == q
+    if d >= 16:
+        assert stats['fallback_queries'] <= max(2, q // 20), stats
+
+
+def test_regression_and_pairwise_order():
+    rng = np.random.default_rng(9)
+    train = rng.standard_normal((6000, 150), dtype=np.float32)          # C order -> numpy pairwise summation
+    test = rng.standard_normal((200, 150), dtype=np.float32)
+    labels = rng.standard_normal(6000)
+    pred, idx, dist, stats = _run(train, labels, test, 10, task='regression', gamma=0.5)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, 10, 0.5, 'regression')
+    assert stats['fallback_queries'] <= 10, stats
+
+
+def test_uncentred_data_is_centred_by_k0():
+    rng = np.random.default_rng(10)
+    train = np.asfortranarray((rng.standard_normal((20000, 64)) + 50.0).astype(np.float32))
+    test = (rng.standard_normal((256, 64)) + 50.0).astype(np.float32)
+    labels = rng.integers(0, 4, 20000)
+    pred, idx, dist, stats = _run(train, labels, test, 10)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, 10, 1, 'classification')
+    assert stats['fallback_queries'] <= 26, stats
+
+
+def test_duplicates_and_ties_fall_back_but_stay_exact():
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 2, (20, 32)).astype(np.float32)
+    train = np.asfortranarray(base[rng.integers(0, 20, 8000)])           # every row duplicated ~400 times
+    test = base[rng.integers(0, 20, 150)]
+    labels = rng.integers(0, 3, 8000)
+    pred, idx, dist, stats = _run(train, labels, test, 10)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, 10, 1, 'classification')
+    assert stats['fallback_queries'] > 0
+
+
+def test_multi_segment_sweep():
+    rng = np.random.default_rng(12)
+    n, d, q, k = 300000, 32, 700, 10
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = rng.standard_normal((q, d), dtype=np.float32)
+    labels = rng.integers(0, 10, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    d_pred, d_idx, d_dist = None, None, None
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    ix.set_option('path', _native.PATH_DIRECT)
+    d_pred, d_idx, d_dist = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    ix.close()
+    assert np.array_equal(idx, d_idx) and np.array_equal(dist, d_dist) and np.array_equal(pred, d_pred)
+    sub = slice(0, 40)
+    parity.assert_matches_oracle(pred[sub], idx[sub], dist[sub], train, labels, test[sub], k, 1, 'classification')
+    assert stats['fallback_queries'] <= q // 20, stats
+
+
+def test_nonfinite_queries_and_train_rows():
+    rng = np.random.default_rng(13)
+    train = np.asfortranarray(rng.standard_normal((4000, 40), dtype=np.float32))
+    test = rng.standard_normal((140, 40), dtype=np.float32)
+    test[5, 3] = np.nan
+    test[77, 0] = np.inf
+    labels = rng.integers(0, 5, 4000)
+    pred, idx, dist, stats = _run(train, labels, test, 7)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, 7, 1, 'classification')
+    train2 = train.copy(order='F')
+    train2[100, 7] = np.inf
+    pred, idx, dist, stats = _run(train2, labels, test, 7)
+    parity.assert_matches_oracle(pred, idx, dist, train2, labels, test, 7, 1, 'classification')
