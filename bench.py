@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the kNN predict hot path (BASELINE.json metric: kNN predict queries/sec, k=10, on B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3]
+
+Workload (default, BASELINE.json configs[3], "C4"): synthetic 1,000,000 x 128 fp32 train set resident on every GPU,
+100,000 fp32 queries per GPU per step, k = 10, classification labels in 0..9 -- the reference's
+KNearestNeighborsClassification.predict (osml/predict.py:805-811).  Queries shard across GPUs with no collective
+(SURVEY.md section 8e), so per-GPU work is fixed as N grows: "scaling": "weak".
+
+One step = one pass of the hot path over one batch of 100,000 queries:
+  value  queries/s with the queries already in HBM (osml_knn_predict_device, CUDA events, max over ranks)
+  e2e    queries/s through the C ABI with HOST buffers (osml_knn_predict: pinned host queries -> H2D -> kernels ->
+         D2H predictions), copies inside the timed region
+  roofline  of the dominant kernel (K1, the tcgen05 filter): algorithmic 2*N*D FLOP per query
+         over its CUDA-event duration, against the measured dense bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference's numpy path on a bounded sample of the same queries, 1 core
+`--impl reference` times that CPU port with every host core it can use and prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, d, queries per GPU per step, k, seed)
+    'c4': (1_000_000, 128, 100_000, 10, 4),
+    'c3': (60_000, 784, 10_000, 10, 3),
+}
+METRIC = 'kNN predict queries/sec (k=10)'
+
+
+def make_data(name, rank):
+    n, d, q, k, seed = WORKLOADS[name]
+    rng = np.random.default_rng(seed)
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))   # DataFrame.values is F-ordered
+    labels = rng.integers(0, 10, n)
+    qrng = np.random.default_rng(seed + 1 + 1000 * rank)
+    queries = qrng.standard_normal((q, d), dtype=np.float32)
+    return train, labels, queries, k
+
+
+def workload_description(name, n_gpus):
+    n, d, q, k, seed = WORKLOADS[name]
+    return {'workload': '%s: synthetic gaussian %dx%d fp32 train (replicated per GPU), %d fp32 queries per GPU per step '
+                        '(%d in total), k=%d, KNearestNeighborsClassification, 10 classes'
+                        % (name.upper(), n, d, q, q * n_gpus, k),
+            'train_rows': n, 'features': d, 'queries_per_gpu_per_step': q, 'k': k, 'task': 'classification',
+            'parallelism': 'query-sharded x%d, no collective' % n_gpus,
+            'l2': 'inputs larger than L2: %.0f MB fp32 train + bf16 filter copy per pass vs 126 MB L2'
+                  % (n * d * 4 / 1e6)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arms: the oracle port of the reference's numpy path (test infrastructure, timed here only as the baseline)
+# ----------------------------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(train, labels, k):
+    _CPU['train'], _CPU['labels'], _CPU['k'] = train, labels, k
+
+
+def _cpu_predict(queries):
+    from oracle import knn_oracle as ko
+    return ko.predict_classification(_CPU['train'], _CPU['labels'], queries, k=_CPU['k'], tie_rule='reference')
+
+
+def cpu_baseline_single_core(train, labels, queries, k, budget_s=20.0):
+    """Reference port on one core (the reference is single-threaded: predict.py:787, 807); bounded sample."""
+    from oracle import knn_oracle as ko
+    t0 = time.perf_counter()
+    ko.predict_classification(train, labels, queries[:1], k=k, tie_rule='reference')
+    per_query = time.perf_counter() - t0
+    sample = int(max(2, min(64, budget_s / max(per_query, 1e-6))))
+    t0 = time.perf_counter()
+    pred = ko.predict_classification(train, labels, queries[:sample], k=k, tie_rule='reference')
+    dt = time.perf_counter() - t0
+    return sample / dt, sample, pred
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the oracle port on all host cores (fork pool, queries split across workers)."""
+    import multiprocessing as mp
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    train, labels, queries, k = make_data(args.workload, 0)
+    cores = len(os.sched_getaffinity(0))
+    _cpu_init(train, labels, k)
+    t0 = time.perf_counter()
+    _cpu_predict(queries[:1])
+    per_query = time.perf_counter() - t0
+    # bounded sample per step: about 4 s of wall clock per step with every core busy
+    per_worker = int(max(1, min(16, 4.0 / max(per_query, 1e-6))))
+    sample = per_worker * cores
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        chunks = [queries[i * per_worker:(i + 1) * per_worker] for i in range(cores)]
+        for _ in range(args.warmup):
+            pool.map(_cpu_predict, chunks)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_predict, chunks)
+        dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {'metric': METRIC, 'value': value, 'unit': 'queries/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': workload_description(args.workload, args.gpus),
+            'cpu_baseline': {'value': value, 'unit': 'queries/s', 'cores': cores, 'kind': 'port',
+                             'sample': '%d queries per step (%d per worker process), numpy oracle port of '
+                                       'osml/predict.py:740-811' % (sample, per_worker)},
+            'e2e': {'value': value, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = []
+        reasons = set()
+        sm_max = None
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                sm_max = float(p[1])
+            except ValueError:
+                continue
+            for name, flag in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[3:7]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': sm_max, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            peaks = json.load(f)
+        return peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops')), peaks.get('hbm_gbs'), 'measured'
+    return 1400.0, 6650.0, 'fallback'   # B200_PROFILING.md: sustained bf16 ~1.4 PFLOP/s, 6.65 TB/s
+
+
+def load_traffic(workload, q):
+    path = os.path.join(ROOT, 'profiles', 'k1_dram_traffic.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        rec = json.load(f)
+    entry = rec.get('%s_q%d' % (workload, q))
+    return entry['dram_bytes_per_launch'] if entry else None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from osml_b200 import _native
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    n_gpus = world
+
+    train, labels, queries, k = make_data(args.workload, rank)
+    n, d = train.shape
+    q = queries.shape[0]
+    index = _native.Index(train, labels, k, 1, 1e-8, device=local_rank)      # = KNearestNeighbors._fit
+    index.set_option('path', _native.PATHS[args.path])
+
+    stream = torch.cuda.current_stream().cuda_stream
+    d_queries = torch.from_numpy(queries).cuda()
+    d_pred = torch.empty(q, dtype=torch.float64, device='cuda')
+    pinned_q = torch.from_numpy(queries).pin_memory()
+    pinned_q_np = pinned_q.numpy()
+    host_pred = torch.empty(q, dtype=torch.float64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        index.predict_device(d_queries.data_ptr(), q, _native.CLASSIFICATION, d_pred.data_ptr(), None, None, stream)
+
+    def e2e_step():
+        return index.predict(pinned_q_np, _native.CLASSIFICATION)
+
+    def timed(step_fn, steps, use_events):
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        filt_ms, filt_launches = 0.0, 0
+        for _ in range(steps):
+            step_fn()
+            st = index.stats()
+            filt_ms += st['last_filter_ms']
+            filt_launches += st['last_filter_launches']
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) if use_events else (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), filt_ms, filt_launches
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    torch.cuda.synchronize()
+    first_pred = d_pred.cpu().numpy().copy()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    index.reset_stats()
+    total_ms, filt_ms, filt_launches = timed(resident_step, args.steps, True)
+    stats = index.stats()
+    launches = stats['kernel_launches']
+    fallback = stats['fallback_queries']
+    clocks = sampler.stop() if rank == 0 else None
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms, _, _ = timed(e2e_step, args.steps, False)
+    e2e_pred = e2e_step()
+    assert np.array_equal(e2e_pred, first_pred), 'host-buffer and device-buffer paths disagree'
+
+    value = q * n_gpus * args.steps / (total_ms / 1e3)
+    e2e_value = q * n_gpus * args.steps / (e2e_ms / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak_tflops, peak_gbs, peak_kind = load_peaks()
+    flop_per_launch = 2.0 * n * d * q * args.steps / max(filt_launches, 1)
+    k1_ms = filt_ms / max(filt_launches, 1)
+    if filt_launches > 0 and k1_ms > 0:
+        achieved = flop_per_launch / (k1_ms / 1e3) / 1e12
+        roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
+                    'frac': achieved / peak_tflops, 'traffic': load_traffic(args.workload, q),
+                    'kernel': 'knn_tc_filter_kernel', 'kernel_ms_per_launch': k1_ms, 'launches_timed': filt_launches,
+                    'kernel_share_of_step': filt_ms / total_ms,
+                    'algorithmic_flop_per_launch': flop_per_launch, 'peak_source': peak_kind + ' bf16 dense, sustained',
+                    'passes': 1, 'note': 'single bf16 pass (K=%d incl. 3 norm columns padded to 16)' % (d + 16)}
+    else:   # direct path only: CUDA-core bound; report against the HBM roofline for completeness
+        roofline = {'bound': 'hbm', 'achieved': None, 'peak': peak_gbs, 'unit': 'GB/s', 'frac': None, 'traffic': None,
+                    'note': 'direct (K2) path is CUDA-core bound: 3 un-fusable instructions per element'}
+
+    cpu_value, cpu_sample, cpu_pred = cpu_baseline_single_core(train, labels, queries, k)
+    parity_ok = bool(np.array_equal(cpu_pred, first_pred[:cpu_sample]))
+
+    line = {'metric': METRIC, 'value': value, 'unit': 'queries/s', 'n_gpus': n_gpus, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_description(args.workload, n_gpus),
+            'e2e': {'value': e2e_value, 'unit': 'queries/s', 'h2d_bytes_per_step': int(queries.nbytes),
+                    'd2h_bytes_per_step': int(q * 8), 'ms_per_step': e2e_ms / args.steps,
+                    'api': 'osml_knn_predict (C ABI, pinned host buffers)'},
+            'gpu_launches': int(launches), 'roofline': roofline,
+            'cpu_baseline': {'value': cpu_value, 'unit': 'queries/s', 'cores': 1, 'kind': 'port',
+                             'sample': '%d of the same queries through the numpy oracle port of '
+                                       'osml/predict.py:740-811 (the reference is single-threaded)' % cpu_sample,
+                             'matches_gpu_predictions': parity_ok},
+            'clocks': clocks, 'fallback_queries_per_step': fallback / args.steps, 'path': args.path}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
+    ap.add_argument('--path', default='auto', choices=['auto', 'direct', 'tensor'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -91,6 +91,9 @@ struct osml_knn_index {
     int label_kind = 0;
     int path = OSML_KNN_PATH_AUTO;
     int slack = -1;
+    int opt_epi_warps = 0;
+    int opt_nseg = 0;
+    int debug = 0;
     int64_t query_block = 0;
 
     DeviceBuffer train;        // row-major n x d, original dtype
@@ -268,6 +271,7 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         osml::TensorLaunch tl;
         tl.train = ix->train.ptr; tl.dtype = ix->dtype; tl.n = ix->n; tl.d = ix->d; tl.k = ix->k;
         tl.sum_order = ix->sum_order; tl.index_base = ix->index_base; tl.slack = ix->slack;
+        tl.opt_epi_warps = ix->opt_epi_warps; tl.opt_nseg = ix->opt_nseg; tl.debug = ix->debug;
         int64_t fallback = 0, launches = 0;
         std::string err;
         int rc = osml::tensor_neighbours(ix->tensor, tl, d_queries, q, out_d, out_i, stream, &fallback, &launches, &err,
@@ -275,10 +279,11 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
                                              return launch_direct(ix, dq, qq, od, oi, stream);
                                          });
         ix->stats.kernel_launches += launches;
-        ix->stats.last_filter_launches += launches;
         if (rc != OSML_KNN_OK) return err.empty() ? rc : fail(rc, err);
         ix->stats.fallback_queries += fallback;
         ix->stats.tensor_queries += q;
+        ix->stats.last_filter_ms = ix->tensor.filter_ms;
+        ix->stats.last_filter_launches = ix->tensor.filter_launches;
         return OSML_KNN_OK;
     }
     return launch_direct(ix, d_queries, q, out_d, out_i, stream);
@@ -442,7 +447,8 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
     CUDA_TRY(cudaStreamSynchronize(ix->stream));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ix->ev0, ix->ev3) == cudaSuccess) ix->stats.last_total_ms = ms;
-    if (cudaEventElapsedTime(&ms, ix->ev1, ix->ev2) == cudaSuccess) ix->stats.last_filter_ms = ms;
+    if (ix->stats.tensor_queries == 0 || ix->tensor.filter_launches == 0)
+        if (cudaEventElapsedTime(&ms, ix->ev1, ix->ev2) == cudaSuccess) ix->stats.last_filter_ms = ms;
     return OSML_KNN_OK;
 }
 
@@ -489,6 +495,9 @@ int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
         return OSML_KNN_OK;
     }
     if (key == "slack") { ix->slack = (int)value; return OSML_KNN_OK; }
+    if (key == "epi_warps") { ix->opt_epi_warps = (int)value; return OSML_KNN_OK; }
+    if (key == "segments") { ix->opt_nseg = (int)value; return OSML_KNN_OK; }
+    if (key == "debug") { ix->debug = (int)value; return OSML_KNN_OK; }
     if (key == "query_block") { ix->query_block = (int64_t)value; return OSML_KNN_OK; }
     return fail(OSML_KNN_EINVAL, "unknown option: " + key);
 }

@@ -59,6 +59,8 @@ struct TcParams {
     int nslot;           // nseg * halves
     float* cand_val;     // [qpad][nslot][kprime]
     int* cand_idx;
+    float* cand_thr;     // [qpad][nslot]: every row the slot dropped has acc <= this (-inf: nothing dropped)
+    int debug;           // ablation switch for profiling: 1 = epilogue skips TMEM loads, 2 = loads but no selection
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -159,24 +161,30 @@ __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int6
 // ---------------------------------------------------------------------------------------------------------------------
 // K1: persistent tcgen05 filter
 // ---------------------------------------------------------------------------------------------------------------------
-struct TcList {
-    float* val; int* idx; int kprime; int stride;     // slot e of this thread at val[e * stride]
-    float thr; int pos_min;
-    __device__ __forceinline__ void reset() {
-        for (int e = 0; e < kprime; ++e) { val[e * stride] = -INFINITY; idx[e * stride] = -1; }
-        thr = -INFINITY; pos_min = 0;
+// Per-thread candidate list in shared memory (slot e of a thread lives e * stride_bytes further on).  The insert runs
+// out of line with scalar register arguments and 32-bit shared addresses, so the hot loop only pays a call when a
+// candidate actually beats the thread's current K'-th best; it returns the new minimum and its slot.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __noinline__ unsigned long long tc_list_insert(uint32_t val_addr, uint32_t idx_addr, int kprime,
+                                                          uint32_t stride_bytes, uint32_t pos_min, float v, int row) {
+    sts_b32(val_addr + pos_min * stride_bytes, __float_as_uint(v));
+    sts_b32(idx_addr + pos_min * stride_bytes, (uint32_t)row);
+    float m = INFINITY;
+    uint32_t pm = 0;
+#pragma unroll 8
+    for (int e = 0; e < kprime; ++e) {
+        const float x = (uint32_t)e == pos_min ? v : lds_f32(val_addr + e * stride_bytes);
+        if (x < m) { m = x; pm = (uint32_t)e; }
     }
-    // precondition v > thr: replaces the current minimum and finds the new one
-    __device__ __noinline__ void insert(float v, int row) {
-        val[pos_min * stride] = v; idx[pos_min * stride] = row;
-        float m = val[0]; int pm = 0;
-        for (int e = 1; e < kprime; ++e) {
-            const float x = val[e * stride];
-            if (x < m) { m = x; pm = e; }
-        }
-        thr = m; pos_min = pm;
-    }
-};
+    return ((unsigned long long)pm << 32) | (unsigned long long)__float_as_uint(m);
+}
 
 __device__ __forceinline__ float tc_max32(const float (&v)[32]) {
     float a0 = ptx::fmax3(v[0], v[1], v[2]), a1 = ptx::fmax3(v[3], v[4], v[5]), a2 = ptx::fmax3(v[6], v[7], v[8]);
@@ -294,40 +302,66 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int cols = kTcBN / halves;                // columns of each tile this thread scans
         const int et = ew * 32 + lane;                  // epilogue thread id
         const int m = quarter * 32 + lane;              // query row inside the tile == TMEM lane
-        TcList list;
-        list.val = list_val + et; list.idx = list_idx + et; list.kprime = p.kprime; list.stride = epi_threads;
+        const uint32_t stride_bytes = (uint32_t)epi_threads * 4;
+        const uint32_t val_addr = ptx::smem_u32(list_val + et), idx_addr = ptx::smem_u32(list_idx + et);
         uint32_t acc_it = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int seg = item / p.nqt, qt = item % p.nqt;
             const int tile0 = seg * p.tiles_per_seg;
             const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
-            list.reset();
+            for (int e = 0; e < p.kprime; ++e) {
+                sts_b32(val_addr + e * stride_bytes, __float_as_uint(-INFINITY));
+                sts_b32(idx_addr + e * stride_bytes, 0xffffffffu);
+            }
+            float thr = -INFINITY;
+            uint32_t pos_min = 0;
+            auto scan = [&](const float (&v)[32], int row0) {
+                const float mx = tc_max32(v);
+                if (mx > thr) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (v[i] > thr) {
+                            const unsigned long long r =
+                                tc_list_insert(val_addr, idx_addr, p.kprime, stride_bytes, pos_min, v[i], row0 + i);
+                            thr = __uint_as_float((uint32_t)r);
+                            pos_min = (uint32_t)(r >> 32);
+                        }
+                    }
+                }
+            };
             for (int t = 0; t < ntiles; ++t, ++acc_it) {
                 const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
                 ptx::mbar_wait(&tmem_full[as], aphase);
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
                 const int row_base = (tile0 + t) * kTcBN + half * cols;
-                for (int c = 0; c < cols; c += 32) {
-                    float v[32];
-                    ptx::tmem_ld_32x32(taddr + c, v);
-                    ptx::tmem_ld_wait();
-                    const float mx = tc_max32(v);
-                    if (mx > list.thr) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (v[i] > list.thr) list.insert(v[i], row_base + c + i);
+                float va[32], vb[32];
+                if (p.debug != 1) {
+                    ptx::tmem_ld_32x32(taddr, va);
+                    for (int c = 0; c < cols; c += 64) {      // two 32-column chunks per trip, loads one chunk ahead
+                        ptx::tmem_ld_wait();
+                        ptx::tmem_ld_32x32(taddr + c + 32, vb);
+                        if (p.debug != 2) scan(va, row_base + c);
+                        else if (va[0] + va[31] == 12345.678f) thr = va[0];
+                        ptx::tmem_ld_wait();
+                        if (c + 64 < cols) ptx::tmem_ld_32x32(taddr + c + 64, va);
+                        if (p.debug != 2) scan(vb, row_base + c + 32);
+                        else if (vb[0] + vb[31] == 12345.678f) thr = vb[0];
                     }
                 }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&tmem_empty[as]);
             }
-            // publish this (query, slot) list
+            // publish this (query, slot) list and the bound on everything it dropped
             const size_t q = (size_t)qt * kTcBM + m;
             const size_t slot = (size_t)seg * halves + half;
             float* ov = p.cand_val + (q * p.nslot + slot) * p.kprime;
             int* oi = p.cand_idx + (q * p.nslot + slot) * p.kprime;
-            for (int e = 0; e < p.kprime; ++e) { ov[e] = list.val[e * list.stride]; oi[e] = list.idx[e * list.stride]; }
+            for (int e = 0; e < p.kprime; ++e) {
+                ov[e] = lds_f32(val_addr + e * stride_bytes);
+                oi[e] = (int)__float_as_uint(lds_f32(idx_addr + e * stride_bytes));
+            }
+            p.cand_thr[q * p.nslot + slot] = thr;
         }
     }
     ptx::tc_fence_before();
@@ -353,7 +387,7 @@ constexpr int kRescoreWarps = 4;
 __global__ void __launch_bounds__(32 * kRescoreWarps)
 knn_rescore_kernel(const float* __restrict__ train, const float* __restrict__ queries, int d, int sum_order,
                    int64_t q_count, int ksel, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
-                   int nslot, int kprime, const double* __restrict__ qnorm2, const double* __restrict__ qerr,
+                   const float* __restrict__ cand_thr, int nslot, int kprime, const double* __restrict__ qnorm2, const double* __restrict__ qerr,
                    TcBounds bounds, int64_t index_base, float* __restrict__ out_d, int64_t* __restrict__ out_i,
                    int* __restrict__ flags) {
     __shared__ float s_dist[kRescoreWarps][kTcMaxCand];
@@ -363,7 +397,6 @@ knn_rescore_kernel(const float* __restrict__ train, const float* __restrict__ qu
     const int64_t q = (int64_t)blockIdx.x * kRescoreWarps + warp;
     if (q >= q_count) return;
     const int ncand = nslot * kprime;
-    const float* cv = cand_val + (size_t)q * ncand;
     const int* ci = cand_idx + (size_t)q * ncand;
     const float* qrow = queries + (size_t)q * d;
     float* dist = s_dist[warp];
@@ -405,13 +438,8 @@ knn_rescore_kernel(const float* __restrict__ train, const float* __restrict__ qu
         const double qn = sqrt(n2);
         const double eps = bounds.c_mma * (qn * bounds.tnorm_max + 0.5 * bounds.tnorm_max * bounds.tnorm_max);
         for (int s = lane; s < nslot; s += 32) {
-            float thr = INFINITY;
-            bool full = true;
-            for (int e = 0; e < kprime; ++e) {
-                if (ci[s * kprime + e] < 0) full = false;
-                thr = fminf(thr, cv[s * kprime + e]);
-            }
-            if (!full) continue;              // fewer than K' real rows in this slot: nothing was dropped
+            const float thr = cand_thr[(size_t)q * nslot + s];
+            if (thr == -INFINITY) continue;   // the slot never filled its list: nothing was dropped
             const double l2 = n2 - 2.0 * ((double)thr + eps);
             const double lower = (sqrt(fmax(l2, 0.0)) - (eq + bounds.et_max)) * (1.0 - bounds.gamma);
             if (!(lower > dk)) ok = false;    // also catches NaN
@@ -471,15 +499,21 @@ struct TensorState {
     int64_t npad = 0; int dp = 0;
     double et_max = 0.0, tnorm_max = 0.0;
     TcBuffer train_bf16, center, stats, partial;
-    TcBuffer q_bf16, q_norm2, q_err, cand_val, cand_idx, flags, fb_list, fb_count, fb_queries, fb_d, fb_i;
+    TcBuffer q_bf16, q_norm2, q_err, cand_val, cand_idx, cand_thr, flags, fb_list, fb_count, fb_queries, fb_d, fb_i;
     CUtensorMap map_b;
     void* encode_fn = nullptr;
     int sm_count = 0;
     int smem_optin = 0;
+    cudaEvent_t ev_k1_begin = nullptr, ev_k1_end = nullptr;
+    double filter_ms = 0.0;       // device time of the K1 launches of the last neighbour search (CUDA events)
+    int64_t filter_launches = 0;
 };
 
 struct TensorLaunch {
     const void* train; int dtype; int64_t n, d; int k; int sum_order; int64_t index_base; int slack;
+    int opt_epi_warps = 0;   // 0 = auto, else 4 or 8
+    int opt_nseg = 0;        // 0 = auto
+    int debug = 0;
 };
 
 using DirectFallback = std::function<int(const void*, int64_t, void*, int64_t*)>;
@@ -502,14 +536,17 @@ inline bool tensor_path_supported(int dtype, int64_t n, int64_t d, int k) {
 
 inline size_t tensor_bytes(const TensorState& s) {
     return s.train_bf16.cap + s.center.cap + s.stats.cap + s.partial.cap + s.q_bf16.cap + s.q_norm2.cap + s.q_err.cap +
-           s.cand_val.cap + s.cand_idx.cap + s.flags.cap + s.fb_list.cap + s.fb_count.cap + s.fb_queries.cap +
+           s.cand_val.cap + s.cand_idx.cap + s.cand_thr.cap + s.flags.cap + s.fb_list.cap + s.fb_count.cap + s.fb_queries.cap +
            s.fb_d.cap + s.fb_i.cap;
 }
 
 inline void tensor_release(TensorState& s) {
     for (TcBuffer* b : {&s.train_bf16, &s.center, &s.stats, &s.partial, &s.q_bf16, &s.q_norm2, &s.q_err, &s.cand_val,
-                        &s.cand_idx, &s.flags, &s.fb_list, &s.fb_count, &s.fb_queries, &s.fb_d, &s.fb_i})
+                        &s.cand_idx, &s.cand_thr, &s.flags, &s.fb_list, &s.fb_count, &s.fb_queries, &s.fb_d, &s.fb_i})
         b->release();
+    if (s.ev_k1_begin) cudaEventDestroy(s.ev_k1_begin);
+    if (s.ev_k1_end) cudaEventDestroy(s.ev_k1_end);
+    s.ev_k1_begin = s.ev_k1_end = nullptr;
     s.ready = false;
 }
 
@@ -604,7 +641,8 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     const int ksel = tl.k + 1;
     const int kprime = tc_kprime(tl.k, tl.slack);
     if (kprime > kTcMaxKPrime) { if (err) *err = "k + 1 + slack exceeds 64"; return 4; }
-    const int epi_warps = kprime <= 24 ? 8 : 4;
+    int epi_warps = kprime <= 24 ? 8 : 4;
+    if (tl.opt_epi_warps == 4 || (tl.opt_epi_warps == 8 && kprime <= 24)) epi_warps = tl.opt_epi_warps;
     const int halves = epi_warps / 4;
     const int64_t qpad = (q + kTcBM - 1) / kTcBM * kTcBM;
     const int nqt = (int)(qpad / kTcBM);
@@ -613,8 +651,11 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     const int ksteps = (d + 3 + 15) / 16;
 
     // segments: enough (query tile, segment) items to balance the persistent grid, few enough to keep K3 cheap
+    // every extra segment restarts the per-query threshold (more list inserts, more candidates for K3), so use the
+    // fewest that still give every SM an item; with more query tiles than SMs a single sweep per tile is best
     int max_seg_by_cand = std::max(1, kTcMaxCand / (kprime * halves));
-    int nseg = (3 * st.sm_count + nqt - 1) / nqt;
+    int nseg = nqt >= st.sm_count ? 1 : (st.sm_count + nqt - 1) / nqt;
+    if (tl.opt_nseg > 0) nseg = tl.opt_nseg;
     nseg = std::max(1, std::min(nseg, std::min(max_seg_by_cand, std::max(1, tiles_total / 8))));
     int tiles_per_seg = (tiles_total + nseg - 1) / nseg;
     nseg = (tiles_total + tiles_per_seg - 1) / tiles_per_seg;
@@ -632,6 +673,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     TC_TRY(st.q_err.reserve((size_t)qpad * sizeof(double)));
     TC_TRY(st.cand_val.reserve((size_t)qpad * nslot * kprime * sizeof(float)));
     TC_TRY(st.cand_idx.reserve((size_t)qpad * nslot * kprime * sizeof(int)));
+    TC_TRY(st.cand_thr.reserve((size_t)qpad * nslot * sizeof(float)));
     TC_TRY(st.flags.reserve((size_t)q * sizeof(int)));
     TC_TRY(st.fb_list.reserve((size_t)q * sizeof(int)));
     TC_TRY(st.fb_count.reserve(sizeof(int)));
@@ -651,11 +693,18 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     p.nkb = nkb; p.ksteps = ksteps; p.nqt = nqt; p.nseg = nseg; p.tiles_per_seg = tiles_per_seg;
     p.tiles_total = tiles_total; p.kprime = kprime; p.epi_warps = epi_warps; p.stages = stages; p.nslot = nslot;
     p.cand_val = st.cand_val.as<float>(); p.cand_idx = st.cand_idx.as<int>();
+    p.cand_thr = st.cand_thr.as<float>();
+    p.debug = tl.debug;
     TC_TRY(cudaFuncSetAttribute(knn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min(nqt * nseg, st.sm_count);
+    if (!st.ev_k1_begin) { TC_TRY(cudaEventCreate(&st.ev_k1_begin)); TC_TRY(cudaEventCreate(&st.ev_k1_end)); }
+    TC_TRY(cudaEventRecord(st.ev_k1_begin, stream));
     knn_tc_filter_kernel<<<grid, kTcThreads, smem, stream>>>(map_a, st.map_b, p);
+    TC_TRY(cudaEventRecord(st.ev_k1_end, stream));
     ++*launches;
+    ++st.filter_launches;
     TC_TRY(cudaGetLastError());
+    if (tl.debug) return 0;   // profiling ablations: results are meaningless, skip rescoring
 
     TcBounds b;
     b.et_max = st.et_max; b.tnorm_max = st.tnorm_max;
@@ -664,7 +713,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     TC_TRY(cudaMemsetAsync(st.fb_count.ptr, 0, sizeof(int), stream));
     knn_rescore_kernel<<<(unsigned)((q + kRescoreWarps - 1) / kRescoreWarps), 32 * kRescoreWarps, 0, stream>>>(
         static_cast<const float*>(tl.train), d_queries, d, tl.sum_order, q, ksel, st.cand_val.as<float>(),
-        st.cand_idx.as<int>(), nslot, kprime, st.q_norm2.as<double>(), st.q_err.as<double>(), b, tl.index_base, out_d,
+        st.cand_idx.as<int>(), st.cand_thr.as<float>(), nslot, kprime, st.q_norm2.as<double>(), st.q_err.as<double>(), b, tl.index_base, out_d,
         out_i, st.flags.as<int>());
     tc_compact_flags_kernel<<<(unsigned)((q + 255) / 256), 256, 0, stream>>>(st.flags.as<int>(), q, st.fb_list.as<int>(),
                                                                              st.fb_count.as<int>());
@@ -673,6 +722,10 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     int count = 0;
     TC_TRY(cudaMemcpyAsync(&count, st.fb_count.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
     TC_TRY(cudaStreamSynchronize(stream));
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, st.ev_k1_begin, st.ev_k1_end) == cudaSuccess) st.filter_ms += ms;
+    }
     if (count > 0) {
         TC_TRY(st.fb_queries.reserve((size_t)count * d * sizeof(float)));
         TC_TRY(st.fb_d.reserve((size_t)count * ksel * sizeof(float)));
@@ -696,6 +749,8 @@ inline int tensor_neighbours(TensorState& st, const TensorLaunch& tl, const void
                              std::string* err, const DirectFallback& direct) {
     int rc = tc_prepare(st, tl, stream, launches, err);
     if (rc) return rc;
+    st.filter_ms = 0.0;
+    st.filter_launches = 0;
     if (!st.usable) {                       // non-finite train rows: the filter's bounds do not hold
         *fallback += q;
         return direct(d_queries, q, out_d, out_i);

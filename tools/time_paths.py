@@ -13,6 +13,7 @@ def main():
     n, d, q, k = (int(x) for x in sys.argv[1:5])
     path = sys.argv[5] if len(sys.argv) > 5 else 'direct'
     reps = int(sys.argv[6]) if len(sys.argv) > 6 else 3
+    opts = dict(a.split('=') for a in sys.argv[7:])
     rng = np.random.default_rng(0)
     train = rng.standard_normal((n, d), dtype=np.float32)
     labels = rng.integers(0, 10, n)
@@ -20,6 +21,8 @@ def main():
     t0 = time.time()
     ix = _native.Index(train, labels, k, 1, 1e-8)
     ix.set_option('path', _native.PATHS[path])
+    for key, value in opts.items():
+        ix.set_option(key, float(value))
     print('create %.3fs' % (time.time() - t0))
     dq = torch.from_numpy(test).cuda()
     out = torch.empty(q, dtype=torch.float64, device='cuda')
