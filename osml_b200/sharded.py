@@ -1,0 +1,153 @@
+"""Multi-GPU host logic: one process per GPU (torchrun), `torch.distributed` for the plumbing.
+
+The reference has no multi-device story; the two modes below are the ones north_star names
+(SURVEY.md section 8e):
+
+* **query-sharded** (`predict_query_sharded`): the train set is replicated, every rank answers a contiguous block of
+  ceil(Q / G) queries, the per-rank predictions are all-gathered (Q doubles -- the only exchange, and only so that
+  every rank returns the full Series like the reference would).  No data-path collective.
+* **train-sharded** (`TrainShardedIndex`): rank r holds train rows [r * ceil(N / G), ...) plus the full label vector.
+  Every rank runs the neighbour search over all queries on its rows (exact distances in the oracle's arithmetic,
+  global row indices), the partial (k+1)-lists are exchanged with ONE all-gather over NCCL / NVLink, and each rank
+  merges the G lists per query by (distance, index) and aggregates.  The merge is exact, so the result is
+  bit-identical to the single-GPU one.
+
+The arithmetic is always the CUDA path (`NativeBackend`); the `backend_factory` argument exists so the collective and
+slicing logic can be exercised on CPU with gloo in tests/test_dist_gloo.py (with a test double, never in production).
+"""
+import numpy as np
+
+from osml_b200 import _native
+
+
+def split_bounds(n, parts):
+    """Contiguous blocks of ceil(n / parts): [(lo, hi)] * parts (trailing blocks may be empty)."""
+    step = -(-n // parts)
+    return [(min(n, r * step), min(n, (r + 1) * step)) for r in range(parts)]
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _world(group=None):
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+class NativeBackend:
+    """The CUDA path behind the C ABI, speaking torch CUDA tensors for the collective."""
+
+    def __init__(self, train_shard, labels_full, k, rbf_gamma, epsilon, index_base, device, sum_order, path='auto'):
+        import torch
+        self.torch = torch
+        self.device = torch.device('cuda', device)
+        self.index = _native.Index(train_shard, labels_full, k, rbf_gamma, epsilon, device=device,
+                                   index_base=index_base, sum_order=sum_order)
+        self.index.set_option('path', _native.PATHS[path])
+        self.k = int(k)
+        self.dist_dtype = torch.float32 if self.index.dist_dtype == np.float32 else torch.float64
+
+    def neighbours(self, queries):
+        torch = self.torch
+        q = queries.shape[0]
+        with torch.cuda.device(self.device):
+            d_q = torch.from_numpy(np.ascontiguousarray(queries)).to(self.device)
+            idx = torch.empty((q, self.k + 1), dtype=torch.int64, device=self.device)
+            dist = torch.empty((q, self.k + 1), dtype=self.dist_dtype, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.index.neighbours_device(d_q.data_ptr(), q, idx.data_ptr(), dist.data_ptr(), stream)
+        return idx, dist
+
+    def merge_predict(self, parts_idx, parts_dist, task):
+        torch = self.torch
+        parts, q = parts_idx.shape[0], parts_idx.shape[1]
+        with torch.cuda.device(self.device):
+            pred = torch.empty(q, dtype=torch.float64, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.index.merge_predict_device(parts_idx.data_ptr(), parts_dist.data_ptr(), parts, q, task,
+                                            pred.data_ptr(), None, None, stream)
+            return pred.cpu().numpy()
+
+    def close(self):
+        self.index.close()
+
+
+class TrainShardedIndex:
+    """Train rows sharded across the ranks of `group`; predictions bit-identical to the unsharded index."""
+
+    def __init__(self, train, labels, k, rbf_gamma=1, epsilon=1e-8, device=None, group=None, backend_factory=None,
+                 query_block=131072, path='auto'):
+        train = np.asarray(train)
+        self.world, self.rank = _world(group)
+        self.group = group
+        self.n = train.shape[0]
+        self.k = int(k)
+        if self.n < self.k + 1:
+            raise ValueError                                  # predict.py:768-769 on the *global* row count
+        self.bounds = split_bounds(self.n, self.world)
+        lo, hi = self.bounds[self.rank]
+        if hi <= lo:
+            raise ValueError('rank %d would hold no training rows' % self.rank)
+        sum_order = _native.sum_order_of(train)               # layout of the whole matrix decides the order
+        shard = train[lo:hi]
+        if device is None:
+            from osml_b200.predict import _default_device
+            device = _default_device()
+        factory = backend_factory or NativeBackend
+        self.backend = factory(shard, np.ascontiguousarray(labels), k, rbf_gamma, epsilon, lo, device, sum_order,
+                               path)
+        self.query_block = int(query_block)
+
+    def predict(self, queries, task):
+        """queries: the same (Q, D) matrix on every rank.  Returns the fp64 predictions for all Q on every rank."""
+        queries = np.asarray(queries)
+        if self.n < self.k + 2:
+            raise ValueError                                  # np.argpartition(d, k + 1) needs k + 1 < N
+        out = np.empty(queries.shape[0], dtype=np.float64)
+        for q0 in range(0, queries.shape[0], self.query_block):
+            block = queries[q0:q0 + self.query_block]
+            idx, dist_ = self.backend.neighbours(block)
+            if self.world > 1:
+                dist = _dist()
+                import torch
+                qb, ksel = idx.shape
+                all_idx = torch.empty((self.world * qb, ksel), dtype=idx.dtype, device=idx.device)
+                all_dist = torch.empty((self.world * qb, ksel), dtype=dist_.dtype, device=dist_.device)
+                dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=self.group)
+                dist.all_gather_into_tensor(all_dist, dist_.contiguous(), group=self.group)
+                all_idx = all_idx.view(self.world, qb, ksel)          # [part][q][k+1], the C ABI's merge layout
+                all_dist = all_dist.view(self.world, qb, ksel)
+            else:
+                all_idx, all_dist = idx[None], dist_[None]
+            out[q0:q0 + block.shape[0]] = self.backend.merge_predict(all_idx, all_dist, task)
+        return out
+
+    def close(self):
+        self.backend.close()
+
+
+def predict_query_sharded(predict_block, n_queries, group=None, comm_device=None):
+    """Runs `predict_block(lo, hi) -> fp64 array` on this rank's block of queries and all-gathers the predictions so
+    that every rank returns all `n_queries` of them.  `predict_block` is typically
+    ``lambda lo, hi: model._ensure_index().predict(values[lo:hi], task)``."""
+    world, rank = _world(group)
+    bounds = split_bounds(n_queries, world)
+    lo, hi = bounds[rank]
+    mine = np.asarray(predict_block(lo, hi), dtype=np.float64) if hi > lo else np.zeros(0)
+    if world == 1:
+        return mine
+    import torch
+    dist = _dist()
+    step = bounds[0][1] - bounds[0][0]
+    if comm_device is None:
+        comm_device = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' \
+            else torch.device('cpu')
+    send = torch.zeros(step, dtype=torch.float64, device=comm_device)
+    send[:hi - lo] = torch.from_numpy(mine).to(comm_device)
+    recv = torch.empty(world * step, dtype=torch.float64, device=comm_device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv.cpu().numpy()[:n_queries].copy() if world * step >= n_queries else None
