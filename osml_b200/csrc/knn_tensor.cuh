@@ -45,6 +45,7 @@ constexpr int kTcThreads = 384;       // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle
 constexpr int kTcMaxKPrime = 64;
 constexpr int kTcMaxCand = 512;       // candidates per query K3 handles (slots * K')
 constexpr float kTcPadScore = -3.0e38f;
+constexpr int tc_cta_group = 1;       // CTAs cooperating on one work item
 
 struct TcParams {
     int nkb;             // K blocks of the padded feature dimension
@@ -196,6 +197,74 @@ __device__ __forceinline__ float tc_max32(const float (&v)[32]) {
     return fmaxf(ptx::fmax3(b0, b1, b2), b3);
 }
 
+__device__ __forceinline__ float tc_sel_below(float x, float cur) { return x < cur ? x : -INFINITY; }
+
+// largest of the 32 values that is strictly below `cur`
+__device__ __forceinline__ float tc_next_below(const float (&v)[32], float cur) {
+    float a[11];
+#pragma unroll
+    for (int g = 0; g < 10; ++g)
+        a[g] = ptx::fmax3(tc_sel_below(v[3 * g], cur), tc_sel_below(v[3 * g + 1], cur), tc_sel_below(v[3 * g + 2], cur));
+    a[10] = fmaxf(tc_sel_below(v[30], cur), tc_sel_below(v[31], cur));
+    const float b0 = ptx::fmax3(a[0], a[1], a[2]), b1 = ptx::fmax3(a[3], a[4], a[5]), b2 = ptx::fmax3(a[6], a[7], a[8]);
+    return fmaxf(ptx::fmax3(b0, b1, b2), fmaxf(a[9], a[10]));
+}
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+template <int KP>
+__device__ __forceinline__ float tc_list_min(const float (&lv)[KP]) {
+    float m = lv[0];
+#pragma unroll
+    for (int e = 1; e + 1 < KP; e += 2) m = fmin3(m, lv[e], lv[e + 1]);
+    if ((KP & 1) == 0) m = fminf(m, lv[KP - 1]);
+    return m;
+}
+
+// Register-resident candidate list (KP = 16 or 32 entries per thread).
+// Values are "packed": the low log2(KP) mantissa bits of a list entry hold its slot number, and the low 5 bits of an
+// accumulator read from TMEM are replaced by its column inside the 32-column chunk, so a max / min tree returns the
+// value and where it lives in one go.  The perturbation (<= 2^-18 relative) is part of the error budget K3 proves
+// completeness with (TcBounds::c_mma).  All 32 lanes of a warp run the insert rounds together, so a chunk costs
+// max-over-lanes (not sum-over-lanes) of the number of hits.
+template <int KP>
+struct TcRegList {
+    static constexpr uint32_t kSlotMask = KP - 1;
+    float lv[KP];
+    int lr[KP];
+    float thr;
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int e = 0; e < KP; ++e) { lv[e] = __uint_as_float((0xFF7FFFFFu & ~kSlotMask) | (uint32_t)e); lr[e] = -1; }
+        thr = tc_list_min<KP>(lv);
+    }
+    __device__ __forceinline__ void scan(float (&v)[32], int row0) {
+        const float mx = tc_max32(v);
+        if (__any_sync(0xffffffffu, mx > thr)) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float((__float_as_uint(v[i]) & ~31u) | (uint32_t)i);
+            float cur = tc_max32(v);
+            while (__any_sync(0xffffffffu, cur > thr)) {
+                if (cur > thr) {
+                    const uint32_t slot = __float_as_uint(thr) & kSlotMask;
+                    const float nv = __uint_as_float((__float_as_uint(cur) & ~kSlotMask) | slot);
+                    const int row = row0 + (int)(__float_as_uint(cur) & 31u);
+#pragma unroll
+                    for (int e = 0; e < KP; ++e)
+                        if (slot == (uint32_t)e) { lv[e] = nv; lr[e] = row; }
+                    thr = tc_list_min<KP>(lv);
+                }
+                cur = tc_next_below(v, cur);
+            }
+        }
+    }
+};
+
+template <int KP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const TcParams p) {
@@ -204,9 +273,10 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     unsigned char* a_smem = smem;
     unsigned char* b_smem = a_smem + (size_t)p.nkb * kTcABlockBytes;
     const int epi_threads = p.epi_warps * 32;
+    const size_t list_elems = KP > 0 ? 0 : (size_t)p.kprime * epi_threads;   // register lists need no shared memory
     float* list_val = reinterpret_cast<float*>(b_smem + (size_t)p.stages * kTcBStageBytes);
-    int* list_idx = reinterpret_cast<int*>(list_val + (size_t)p.kprime * epi_threads);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(list_idx + (size_t)p.kprime * epi_threads);
+    int* list_idx = reinterpret_cast<int*>(list_val + list_elems);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(list_idx + list_elems);
     uint64_t* full_bar = bars;                    // [stages]
     uint64_t* empty_bar = bars + 8;               // [stages]
     uint64_t* tmem_full = bars + 16;              // [2]
@@ -302,66 +372,114 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int cols = kTcBN / halves;                // columns of each tile this thread scans
         const int et = ew * 32 + lane;                  // epilogue thread id
         const int m = quarter * 32 + lane;              // query row inside the tile == TMEM lane
-        const uint32_t stride_bytes = (uint32_t)epi_threads * 4;
-        const uint32_t val_addr = ptx::smem_u32(list_val + et), idx_addr = ptx::smem_u32(list_idx + et);
         uint32_t acc_it = 0;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const int seg = item / p.nqt, qt = item % p.nqt;
-            const int tile0 = seg * p.tiles_per_seg;
-            const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
-            for (int e = 0; e < p.kprime; ++e) {
-                sts_b32(val_addr + e * stride_bytes, __float_as_uint(-INFINITY));
-                sts_b32(idx_addr + e * stride_bytes, 0xffffffffu);
-            }
-            float thr = -INFINITY;
-            uint32_t pos_min = 0;
-            auto scan = [&](const float (&v)[32], int row0) {
-                const float mx = tc_max32(v);
-                if (mx > thr) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (v[i] > thr) {
-                            const unsigned long long r =
-                                tc_list_insert(val_addr, idx_addr, p.kprime, stride_bytes, pos_min, v[i], row0 + i);
-                            thr = __uint_as_float((uint32_t)r);
-                            pos_min = (uint32_t)(r >> 32);
+        if constexpr (KP > 0) {
+            TcRegList<KP> list;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int seg = item / p.nqt, qt = item % p.nqt;
+                const int tile0 = seg * p.tiles_per_seg;
+                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+                list.reset();
+                for (int t = 0; t < ntiles; ++t, ++acc_it) {
+                    const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                    ptx::mbar_wait(&tmem_full[as], aphase);
+                    ptx::tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
+                    const int row_base = (tile0 + t) * kTcBN + half * cols;
+                    if (p.debug != 1) {
+                        if constexpr (KP <= 16) {
+                            float va[32], vb[32];
+                            ptx::tmem_ld_32x32(taddr, va);
+                            for (int c = 0; c < cols; c += 64) {   // two chunks per trip, loads one chunk ahead
+                                ptx::tmem_ld_wait();
+                                ptx::tmem_ld_32x32(taddr + c + 32, vb);
+                                list.scan(va, row_base + c);
+                                ptx::tmem_ld_wait();
+                                if (c + 64 < cols) ptx::tmem_ld_32x32(taddr + c + 64, va);
+                                list.scan(vb, row_base + c + 32);
+                            }
+                        } else {
+                            for (int c = 0; c < cols; c += 32) {
+                                float va[32];
+                                ptx::tmem_ld_32x32(taddr + c, va);
+                                ptx::tmem_ld_wait();
+                                list.scan(va, row_base + c);
+                            }
                         }
                     }
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&tmem_empty[as]);
                 }
-            };
-            for (int t = 0; t < ntiles; ++t, ++acc_it) {
-                const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
-                ptx::mbar_wait(&tmem_full[as], aphase);
-                ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
-                const int row_base = (tile0 + t) * kTcBN + half * cols;
-                float va[32], vb[32];
-                if (p.debug != 1) {
-                    ptx::tmem_ld_32x32(taddr, va);
-                    for (int c = 0; c < cols; c += 64) {      // two 32-column chunks per trip, loads one chunk ahead
-                        ptx::tmem_ld_wait();
-                        ptx::tmem_ld_32x32(taddr + c + 32, vb);
-                        if (p.debug != 2) scan(va, row_base + c);
-                        else if (va[0] + va[31] == 12345.678f) thr = va[0];
-                        ptx::tmem_ld_wait();
-                        if (c + 64 < cols) ptx::tmem_ld_32x32(taddr + c + 64, va);
-                        if (p.debug != 2) scan(vb, row_base + c + 32);
-                        else if (vb[0] + vb[31] == 12345.678f) thr = vb[0];
+                const size_t q = (size_t)qt * kTcBM + m;
+                const size_t slot = (size_t)seg * halves + half;
+                float* ov = p.cand_val + (q * p.nslot + slot) * KP;
+                int* oi = p.cand_idx + (q * p.nslot + slot) * KP;
+                bool full = true;
+#pragma unroll
+                for (int e = 0; e < KP; ++e) { ov[e] = list.lv[e]; oi[e] = list.lr[e]; full = full && list.lr[e] >= 0; }
+                p.cand_thr[q * p.nslot + slot] = full ? list.thr : -INFINITY;
+            }
+        } else {
+            const uint32_t stride_bytes = (uint32_t)epi_threads * 4;
+            const uint32_t val_addr = ptx::smem_u32(list_val + et), idx_addr = ptx::smem_u32(list_idx + et);
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int seg = item / p.nqt, qt = item % p.nqt;
+                const int tile0 = seg * p.tiles_per_seg;
+                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+                for (int e = 0; e < p.kprime; ++e) {
+                    sts_b32(val_addr + e * stride_bytes, __float_as_uint(-INFINITY));
+                    sts_b32(idx_addr + e * stride_bytes, 0xffffffffu);
+                }
+                float thr = -INFINITY;
+                uint32_t pos_min = 0;
+                auto scan = [&](const float (&v)[32], int row0) {
+                    const float mx = tc_max32(v);
+                    if (mx > thr) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (v[i] > thr) {
+                                const unsigned long long r =
+                                    tc_list_insert(val_addr, idx_addr, p.kprime, stride_bytes, pos_min, v[i], row0 + i);
+                                thr = __uint_as_float((uint32_t)r);
+                                pos_min = (uint32_t)(r >> 32);
+                            }
+                        }
                     }
+                };
+                for (int t = 0; t < ntiles; ++t, ++acc_it) {
+                    const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                    ptx::mbar_wait(&tmem_full[as], aphase);
+                    ptx::tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
+                    const int row_base = (tile0 + t) * kTcBN + half * cols;
+                    float va[32], vb[32];
+                    if (p.debug != 1) {
+                        ptx::tmem_ld_32x32(taddr, va);
+                        for (int c = 0; c < cols; c += 64) {      // two 32-column chunks per trip, loads one chunk ahead
+                            ptx::tmem_ld_wait();
+                            ptx::tmem_ld_32x32(taddr + c + 32, vb);
+                            if (p.debug != 2) scan(va, row_base + c);
+                            else if (va[0] + va[31] == 12345.678f) thr = va[0];
+                            ptx::tmem_ld_wait();
+                            if (c + 64 < cols) ptx::tmem_ld_32x32(taddr + c + 64, va);
+                            if (p.debug != 2) scan(vb, row_base + c + 32);
+                            else if (vb[0] + vb[31] == 12345.678f) thr = vb[0];
+                        }
+                    }
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&tmem_empty[as]);
                 }
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(&tmem_empty[as]);
+                // publish this (query, slot) list and the bound on everything it dropped
+                const size_t q = (size_t)qt * kTcBM + m;
+                const size_t slot = (size_t)seg * halves + half;
+                float* ov = p.cand_val + (q * p.nslot + slot) * p.kprime;
+                int* oi = p.cand_idx + (q * p.nslot + slot) * p.kprime;
+                for (int e = 0; e < p.kprime; ++e) {
+                    ov[e] = lds_f32(val_addr + e * stride_bytes);
+                    oi[e] = (int)__float_as_uint(lds_f32(idx_addr + e * stride_bytes));
+                }
+                p.cand_thr[q * p.nslot + slot] = thr;
             }
-            // publish this (query, slot) list and the bound on everything it dropped
-            const size_t q = (size_t)qt * kTcBM + m;
-            const size_t slot = (size_t)seg * halves + half;
-            float* ov = p.cand_val + (q * p.nslot + slot) * p.kprime;
-            int* oi = p.cand_idx + (q * p.nslot + slot) * p.kprime;
-            for (int e = 0; e < p.kprime; ++e) {
-                ov[e] = lds_f32(val_addr + e * stride_bytes);
-                oi[e] = (int)__float_as_uint(lds_f32(idx_addr + e * stride_bytes));
-            }
-            p.cand_thr[q * p.nslot + slot] = thr;
         }
     }
     ptx::tc_fence_before();
@@ -385,7 +503,7 @@ struct TcBounds {
 constexpr int kRescoreWarps = 4;
 
 __global__ void __launch_bounds__(32 * kRescoreWarps)
-knn_rescore_kernel(const float* __restrict__ train, const float* __restrict__ queries, int d, int sum_order,
+knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __restrict__ queries, int d, int sum_order,
                    int64_t q_count, int ksel, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
                    const float* __restrict__ cand_thr, int nslot, int kprime, const double* __restrict__ qnorm2, const double* __restrict__ qerr,
                    TcBounds bounds, int64_t index_base, float* __restrict__ out_d, int64_t* __restrict__ out_i,
@@ -404,7 +522,7 @@ knn_rescore_kernel(const float* __restrict__ train, const float* __restrict__ qu
 
     for (int c = lane; c < ncand; c += 32) {
         const int row = ci[c];
-        if (row >= 0) {
+        if (row >= 0 && row < n) {        // negative: empty slot; >= n: a padding row of the filter copy
             dist[c] = exact_distance<float>(train + (size_t)row * d, qrow, d, sum_order);
             idx[c] = row;
         } else {
@@ -513,6 +631,7 @@ struct TensorLaunch {
     const void* train; int dtype; int64_t n, d; int k; int sum_order; int64_t index_base; int slack;
     int opt_epi_warps = 0;   // 0 = auto, else 4 or 8
     int opt_nseg = 0;        // 0 = auto
+    int opt_smem_lists = 0;  // 1 = force the shared-memory list epilogue
     int debug = 0;
 };
 
@@ -523,7 +642,9 @@ inline int tc_default_slack(int k) { return std::max(5, (k + 1) / 3); }
 inline int tc_kprime(int k, int slack) {
     if (slack < 0) slack = tc_default_slack(k);
     int kp = k + 1 + slack;
-    return (kp + 7) / 8 * 8;
+    if (kp <= 16) return 16;        // register-resident lists come in 16 and 32 entries
+    if (kp <= 32) return 32;
+    return (kp + 7) / 8 * 8;        // shared-memory lists
 }
 
 inline bool tensor_path_supported(int dtype, int64_t n, int64_t d, int k) {
@@ -641,8 +762,9 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     const int ksel = tl.k + 1;
     const int kprime = tc_kprime(tl.k, tl.slack);
     if (kprime > kTcMaxKPrime) { if (err) *err = "k + 1 + slack exceeds 64"; return 4; }
-    int epi_warps = kprime <= 24 ? 8 : 4;
-    if (tl.opt_epi_warps == 4 || (tl.opt_epi_warps == 8 && kprime <= 24)) epi_warps = tl.opt_epi_warps;
+    const bool reg_lists = kprime <= 32 && !tl.opt_smem_lists;
+    int epi_warps = kprime <= 32 ? 8 : 4;
+    if (tl.opt_epi_warps == 4 || (tl.opt_epi_warps == 8 && (reg_lists || kprime <= 24))) epi_warps = tl.opt_epi_warps;
     const int halves = epi_warps / 4;
     const int64_t qpad = (q + kTcBM - 1) / kTcBM * kTcBM;
     const int nqt = (int)(qpad / kTcBM);
@@ -654,14 +776,25 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     // every extra segment restarts the per-query threshold (more list inserts, more candidates for K3), so use the
     // fewest that still give every SM an item; with more query tiles than SMs a single sweep per tile is best
     int max_seg_by_cand = std::max(1, kTcMaxCand / (kprime * halves));
-    int nseg = nqt >= st.sm_count ? 1 : (st.sm_count + nqt - 1) / nqt;
+    int nseg = 1;
+    {
+        // work items = nqt * nseg over sm_count persistent CTAs: pick the split with the least idle tail, charging
+        // 2 % per extra segment for the restarted thresholds
+        double best = 1e30;
+        const int units = std::max(1, st.sm_count / tc_cta_group);
+        for (int cand = 1; cand <= 8; ++cand) {
+            const double items = (double)((nqt + tc_cta_group - 1) / tc_cta_group) * cand;
+            const double cost = std::ceil(items / units) / (items / units) + 0.02 * (cand - 1);
+            if (cost < best - 1e-9) { best = cost; nseg = cand; }
+        }
+    }
     if (tl.opt_nseg > 0) nseg = tl.opt_nseg;
     nseg = std::max(1, std::min(nseg, std::min(max_seg_by_cand, std::max(1, tiles_total / 8))));
     int tiles_per_seg = (tiles_total + nseg - 1) / nseg;
     nseg = (tiles_total + tiles_per_seg - 1) / tiles_per_seg;
     const int nslot = nseg * halves;
 
-    const size_t list_bytes = (size_t)kprime * epi_warps * 32 * 8;
+    const size_t list_bytes = reg_lists ? 0 : (size_t)kprime * epi_warps * 32 * 8;
     const size_t fixed = (size_t)nkb * kTcABlockBytes + list_bytes + 256 + 1024;
     int stages = (int)(((size_t)st.smem_optin - fixed) / kTcBStageBytes);
     stages = std::min(stages, 6);
@@ -695,11 +828,12 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     p.cand_val = st.cand_val.as<float>(); p.cand_idx = st.cand_idx.as<int>();
     p.cand_thr = st.cand_thr.as<float>();
     p.debug = tl.debug;
-    TC_TRY(cudaFuncSetAttribute(knn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kernel = !reg_lists ? knn_tc_filter_kernel<0> : (kprime == 16 ? knn_tc_filter_kernel<16> : knn_tc_filter_kernel<32>);
+    TC_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min(nqt * nseg, st.sm_count);
     if (!st.ev_k1_begin) { TC_TRY(cudaEventCreate(&st.ev_k1_begin)); TC_TRY(cudaEventCreate(&st.ev_k1_end)); }
     TC_TRY(cudaEventRecord(st.ev_k1_begin, stream));
-    knn_tc_filter_kernel<<<grid, kTcThreads, smem, stream>>>(map_a, st.map_b, p);
+    kernel<<<grid, kTcThreads, smem, stream>>>(map_a, st.map_b, p);
     TC_TRY(cudaEventRecord(st.ev_k1_end, stream));
     ++*launches;
     ++st.filter_launches;
@@ -708,11 +842,12 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
 
     TcBounds b;
     b.et_max = st.et_max; b.tnorm_max = st.tnorm_max;
-    b.c_mma = (double)(ksteps * 16 + 8) * 2.384185791015625e-07 + 1.2e-7;   // (K + 8) * 2^-22  + norm split 2^-23
+    // (K + 8) * 2^-22 accumulation + 2^-23 norm split + 2^-17 for the index bits packed into list values
+    b.c_mma = (double)(ksteps * 16 + 8) * 2.384185791015625e-07 + 1.2e-7 + 7.62939453125e-06;
     b.gamma = (double)(d + 4) * 1.1920928955078125e-07;                      // (D + 4) * 2^-23
     TC_TRY(cudaMemsetAsync(st.fb_count.ptr, 0, sizeof(int), stream));
     knn_rescore_kernel<<<(unsigned)((q + kRescoreWarps - 1) / kRescoreWarps), 32 * kRescoreWarps, 0, stream>>>(
-        static_cast<const float*>(tl.train), d_queries, d, tl.sum_order, q, ksel, st.cand_val.as<float>(),
+        static_cast<const float*>(tl.train), tl.n, d_queries, d, tl.sum_order, q, ksel, st.cand_val.as<float>(),
         st.cand_idx.as<int>(), st.cand_thr.as<float>(), nslot, kprime, st.q_norm2.as<double>(), st.q_err.as<double>(), b, tl.index_base, out_d,
         out_i, st.flags.as<int>());
     tc_compact_flags_kernel<<<(unsigned)((q + 255) / 256), 256, 0, stream>>>(st.flags.as<int>(), q, st.fb_list.as<int>(),

@@ -15,7 +15,7 @@ def main():
     reps = int(sys.argv[6]) if len(sys.argv) > 6 else 3
     opts = dict(a.split('=') for a in sys.argv[7:])
     rng = np.random.default_rng(0)
-    train = rng.standard_normal((n, d), dtype=np.float32)
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
     labels = rng.integers(0, 10, n)
     test = rng.standard_normal((q, d), dtype=np.float32)
     t0 = time.time()
