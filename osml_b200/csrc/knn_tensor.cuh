@@ -45,7 +45,6 @@ constexpr int kTcThreads = 384;       // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle
 constexpr int kTcMaxKPrime = 64;
 constexpr int kTcMaxCand = 512;       // candidates per query K3 handles (slots * K')
 constexpr float kTcPadScore = -3.0e38f;
-constexpr int tc_cta_group = 1;       // CTAs cooperating on one work item
 
 struct TcParams {
     int nkb;             // K blocks of the padded feature dimension
@@ -199,15 +198,8 @@ __device__ __forceinline__ float tc_max32(const float (&v)[32]) {
 
 __device__ __forceinline__ float tc_sel_below(float x, float cur) { return x < cur ? x : -INFINITY; }
 
-// largest of the 32 values that is strictly below `cur`
-__device__ __forceinline__ float tc_next_below(const float (&v)[32], float cur) {
-    float a[11];
-#pragma unroll
-    for (int g = 0; g < 10; ++g)
-        a[g] = ptx::fmax3(tc_sel_below(v[3 * g], cur), tc_sel_below(v[3 * g + 1], cur), tc_sel_below(v[3 * g + 2], cur));
-    a[10] = fmaxf(tc_sel_below(v[30], cur), tc_sel_below(v[31], cur));
-    const float b0 = ptx::fmax3(a[0], a[1], a[2]), b1 = ptx::fmax3(a[3], a[4], a[5]), b2 = ptx::fmax3(a[6], a[7], a[8]);
-    return fmaxf(ptx::fmax3(b0, b1, b2), fmaxf(a[9], a[10]));
+__device__ __forceinline__ float tc_max8(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+    return ptx::fmax3(ptx::fmax3(a0, a1, a2), ptx::fmax3(a3, a4, a5), fmaxf(a6, a7));
 }
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
@@ -237,29 +229,46 @@ struct TcRegList {
     float lv[KP];
     int lr[KP];
     float thr;
-    __device__ __forceinline__ void reset() {
+    // empty slots hold -FLT_MAX, or a seed threshold proven elsewhere (values at or below it are never inserted)
+    __device__ __forceinline__ void reset(float seed = -INFINITY) {
+        const uint32_t base = seed > -3.0e38f ? __float_as_uint(seed) : 0xFF7FFFFFu;
 #pragma unroll
-        for (int e = 0; e < KP; ++e) { lv[e] = __uint_as_float((0xFF7FFFFFu & ~kSlotMask) | (uint32_t)e); lr[e] = -1; }
+        for (int e = 0; e < KP; ++e) { lv[e] = __uint_as_float((base & ~kSlotMask) | (uint32_t)e); lr[e] = -1; }
         thr = tc_list_min<KP>(lv);
     }
-    __device__ __forceinline__ void scan(float (&v)[32], int row0) {
-        const float mx = tc_max32(v);
+    __device__ __forceinline__ void insert(float cur, int row) {
+        const uint32_t slot = __float_as_uint(thr) & kSlotMask;
+        const float nv = __uint_as_float((__float_as_uint(cur) & ~kSlotMask) | slot);
+#pragma unroll
+        for (int e = 0; e < KP; ++e)
+            if (slot == (uint32_t)e) { lv[e] = nv; lr[e] = row; }
+        thr = tc_list_min<KP>(lv);
+    }
+    // one group of 8 columns: only entered (warp-uniformly) when some lane has a value above its threshold there
+    template <int G>
+    __device__ __forceinline__ void scan_group(const float (&v)[32], int row0) {
+        float w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = __uint_as_float((__float_as_uint(v[8 * G + j]) & ~7u) | (uint32_t)j);
+        float cur = tc_max8(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+        while (__any_sync(0xffffffffu, cur > thr)) {
+            if (cur > thr) insert(cur, row0 + 8 * G + (int)(__float_as_uint(cur) & 7u));
+            cur = tc_max8(tc_sel_below(w[0], cur), tc_sel_below(w[1], cur), tc_sel_below(w[2], cur),
+                          tc_sel_below(w[3], cur), tc_sel_below(w[4], cur), tc_sel_below(w[5], cur),
+                          tc_sel_below(w[6], cur), tc_sel_below(w[7], cur));
+        }
+    }
+    __device__ __forceinline__ void scan(const float (&v)[32], int row0) {
+        const float g0 = tc_max8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        const float g1 = tc_max8(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+        const float g2 = tc_max8(v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23]);
+        const float g3 = tc_max8(v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]);
+        const float mx = fmaxf(fmaxf(g0, g1), fmaxf(g2, g3));
         if (__any_sync(0xffffffffu, mx > thr)) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float((__float_as_uint(v[i]) & ~31u) | (uint32_t)i);
-            float cur = tc_max32(v);
-            while (__any_sync(0xffffffffu, cur > thr)) {
-                if (cur > thr) {
-                    const uint32_t slot = __float_as_uint(thr) & kSlotMask;
-                    const float nv = __uint_as_float((__float_as_uint(cur) & ~kSlotMask) | slot);
-                    const int row = row0 + (int)(__float_as_uint(cur) & 31u);
-#pragma unroll
-                    for (int e = 0; e < KP; ++e)
-                        if (slot == (uint32_t)e) { lv[e] = nv; lr[e] = row; }
-                    thr = tc_list_min<KP>(lv);
-                }
-                cur = tc_next_below(v, cur);
-            }
+            if (__any_sync(0xffffffffu, g0 > thr)) scan_group<0>(v, row0);
+            if (__any_sync(0xffffffffu, g1 > thr)) scan_group<1>(v, row0);
+            if (__any_sync(0xffffffffu, g2 > thr)) scan_group<2>(v, row0);
+            if (__any_sync(0xffffffffu, g3 > thr)) scan_group<3>(v, row0);
         }
     }
 };
@@ -294,7 +303,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], epi_threads); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], p.epi_warps); }
         ptx::mbar_init(a_full, 1);
         ptx::mbar_init(a_empty, 1);
         ptx::fence_barrier_init();
@@ -321,9 +330,13 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const int row0 = (tile0 + t) * kTcBN;
                     for (int kb = 0; kb < p.nkb; ++kb) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        ptx::mbar_expect_tx(&full_bar[stage], kTcBStageBytes);
-                        ptx::tma_load_2d(b_smem + (size_t)stage * kTcBStageBytes, &map_b, &full_bar[stage], kb * kTcKB,
-                                         row0);
+                        if (p.debug == 3) {                      // ablation: no operand traffic, MMA on stale smem
+                            ptx::mbar_arrive(&full_bar[stage]);
+                        } else {
+                            ptx::mbar_expect_tx(&full_bar[stage], kTcBStageBytes);
+                            ptx::tma_load_2d(b_smem + (size_t)stage * kTcBStageBytes, &map_b, &full_bar[stage],
+                                             kb * kTcKB, row0);
+                        }
                         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -333,7 +346,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (lane == 0) {
             // ===== MMA issuer =====
             const uint32_t idesc = ptx::umma_idesc_bf16(kTcBM, kTcBN);
-            const uint32_t a_addr = ptx::smem_u32(a_smem), b_addr = ptx::smem_u32(b_smem);
+            const uint32_t hi = ptx::umma_desc_hi_k_sw128();
+            const uint32_t a_lo0 = ptx::umma_desc_lo(ptx::smem_u32(a_smem)), b_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_smem));
             uint32_t stage = 0, phase = 0, it = 0, acc_it = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
                 const int seg = item / p.nqt;
@@ -349,12 +363,14 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     for (int kb = 0; kb < p.nkb; ++kb) {
                         ptx::mbar_wait(&full_bar[stage], phase);
                         ptx::tc_fence_after();
-                        const int nks = min(4, p.ksteps - kb * 4);
-                        for (int ks = 0; ks < nks; ++ks) {
-                            const uint64_t da = ptx::umma_desc_k_sw128(a_addr + kb * kTcABlockBytes + ks * 32);
-                            const uint64_t db = ptx::umma_desc_k_sw128(b_addr + stage * kTcBStageBytes + ks * 32);
-                            ptx::umma_bf16_ss(tmem_d, da, db, idesc, (uint32_t)((kb | ks) != 0));
-                        }
+                        const int nks = p.ksteps - kb * 4;
+                        const uint32_t a_lo = a_lo0 + kb * (kTcABlockBytes >> 4);
+                        const uint32_t b_lo = b_lo0 + stage * (kTcBStageBytes >> 4);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            if (ks < nks)
+                                ptx::umma_bf16_ss_lohi(tmem_d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc,
+                                                       (uint32_t)((kb | ks) != 0));
                         ptx::umma_commit(&empty_bar[stage]);       // frees the smem stage when these MMAs retire
                         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                     }
@@ -380,23 +396,26 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int tile0 = seg * p.tiles_per_seg;
                 const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
                 list.reset();
+                if (p.debug == 4) list.thr = INFINITY;   // ablation: fast path only
                 for (int t = 0; t < ntiles; ++t, ++acc_it) {
                     const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
                     ptx::mbar_wait(&tmem_full[as], aphase);
                     ptx::tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
                     const int row_base = (tile0 + t) * kTcBN + half * cols;
-                    if (p.debug != 1) {
+                    if (p.debug != 1 && p.debug != 3) {
                         if constexpr (KP <= 16) {
                             float va[32], vb[32];
                             ptx::tmem_ld_32x32(taddr, va);
                             for (int c = 0; c < cols; c += 64) {   // two chunks per trip, loads one chunk ahead
                                 ptx::tmem_ld_wait();
                                 ptx::tmem_ld_32x32(taddr + c + 32, vb);
-                                list.scan(va, row_base + c);
+                                if (p.debug != 2) list.scan(va, row_base + c);
+                                else if (va[0] + va[31] == 12345.678f) list.thr = va[0];
                                 ptx::tmem_ld_wait();
                                 if (c + 64 < cols) ptx::tmem_ld_32x32(taddr + c + 64, va);
-                                list.scan(vb, row_base + c + 32);
+                                if (p.debug != 2) list.scan(vb, row_base + c + 32);
+                                else if (vb[0] + vb[31] == 12345.678f) list.thr = vb[0];
                             }
                         } else {
                             for (int c = 0; c < cols; c += 32) {
@@ -408,7 +427,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         }
                     }
                     ptx::tc_fence_before();
-                    ptx::mbar_arrive(&tmem_empty[as]);
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
                 }
                 const size_t q = (size_t)qt * kTcBM + m;
                 const size_t slot = (size_t)seg * halves + half;
@@ -453,7 +473,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
                     const int row_base = (tile0 + t) * kTcBN + half * cols;
                     float va[32], vb[32];
-                    if (p.debug != 1) {
+                    if (p.debug != 1 && p.debug != 3) {
                         ptx::tmem_ld_32x32(taddr, va);
                         for (int c = 0; c < cols; c += 64) {      // two 32-column chunks per trip, loads one chunk ahead
                             ptx::tmem_ld_wait();
@@ -467,7 +487,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         }
                     }
                     ptx::tc_fence_before();
-                    ptx::mbar_arrive(&tmem_empty[as]);
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
                 }
                 // publish this (query, slot) list and the bound on everything it dropped
                 const size_t q = (size_t)qt * kTcBM + m;
@@ -487,6 +508,212 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1, CTA-pair variant (cta_group::2): two CTAs of a cluster (= the two SMs of a TPC) work on one item.  Each keeps
+// its own 128-query tile, loads HALF of every 256-row train tile, and the leader issues one M=256 x N=256 UMMA per K
+// step that reads A and B from both SMs.  Per SM this halves the L2 -> shared-memory operand traffic and the
+// shared-memory bytes the tensor core reads per FLOP, which is what limits the single-CTA kernel.
+// Barrier topology (as in CUTLASS / DeepGEMM 2-SM kernels): TMA bytes of both CTAs are credited to the LEADER's
+// full / a_full barriers; tcgen05.commit multicasts to the empty / tmem_full / a_empty barriers of both CTAs; the
+// epilogue threads of both CTAs arrive on the leader's tmem_empty.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kTcBHalfBytes = (kTcBN / 2) * 128;      // 16 KB: this CTA's half of one K block of a train tile
+// a ring stage of the pair kernel holds ALL K blocks of this CTA's half tile (nkb * 16 KB): one barrier round trip and
+// one wait per tile keep the single MMA-issuing thread off the critical path
+
+template <int KP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          const TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* a_smem = smem;
+    unsigned char* b_smem = a_smem + (size_t)p.nkb * kTcABlockBytes;
+    const uint32_t stage_bytes = (uint32_t)p.nkb * kTcBHalfBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full_bar = bars;                    // [stages]  (used in the leader)
+    uint64_t* empty_bar = bars + 8;               // [stages]
+    uint64_t* tmem_full = bars + 16;              // [2]
+    uint64_t* tmem_empty = bars + 18;             // [2]       (used in the leader)
+    uint64_t* a_full = bars + 20;                 //           (used in the leader)
+    uint64_t* a_empty = bars + 21;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int epi_threads = p.epi_warps * 32;
+    const int nqp = p.nqt / 2;                    // query-tile pairs (host pads nqt to even)
+    const int nitems = nqp * p.nseg;
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 2 * p.epi_warps); }
+        ptx::mbar_init(a_full, 2);
+        ptx::mbar_init(a_empty, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc_pair(tmem_slot, 512);
+    ptx::tc_fence_before();
+    ptx::cluster_sync_all();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer (both CTAs): own query tile, own half of each train tile =====
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int item = cluster_id; item < nitems; item += nclusters, ++it) {
+                const int seg = item / nqp, qt = 2 * (item % nqp) + (int)rank;
+                const int tile0 = seg * p.tiles_per_seg;
+                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+                ptx::mbar_wait(a_empty, (it & 1) ^ 1);
+                if (leader) ptx::mbar_expect_tx(a_full, 2u * (uint32_t)p.nkb * kTcABlockBytes);
+                else ptx::mbar_arrive_remote(a_full, 0);
+                for (int kb = 0; kb < p.nkb; ++kb)
+                    ptx::tma_load_2d_pair(a_smem + (size_t)kb * kTcABlockBytes, &map_a, a_full, kb * kTcKB, qt * kTcBM);
+                for (int t = 0; t < ntiles; ++t) {
+                    const int row0 = (tile0 + t) * kTcBN + (int)rank * (kTcBN / 2);
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (p.debug == 3) {                          // ablation: no operand traffic
+                        if (leader) ptx::mbar_arrive(&full_bar[stage]);
+                        else ptx::mbar_arrive_remote(&full_bar[stage], 0);
+                    } else {
+                        if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+                        else ptx::mbar_arrive_remote(&full_bar[stage], 0);
+                        for (int kb = 0; kb < p.nkb; ++kb)
+                            ptx::tma_load_2d_pair(b_smem + (size_t)stage * stage_bytes + (size_t)kb * kTcBHalfBytes,
+                                                  &map_b, &full_bar[stage], kb * kTcKB, row0);
+                    }
+                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ===== MMA issuer (leader CTA only) =====
+            const uint32_t idesc = ptx::umma_idesc_bf16(2 * kTcBM, kTcBN);
+            const uint32_t hi = ptx::umma_desc_hi_k_sw128();
+            const uint32_t a_lo0 = ptx::umma_desc_lo(ptx::smem_u32(a_smem)), b_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_smem));
+            uint32_t stage = 0, phase = 0, it = 0, acc_it = 0;
+            for (int item = cluster_id; item < nitems; item += nclusters, ++it) {
+                const int seg = item / nqp;
+                const int tile0 = seg * p.tiles_per_seg;
+                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+                ptx::mbar_wait(a_full, it & 1);
+                ptx::tc_fence_after();
+                for (int t = 0; t < ntiles; ++t, ++acc_it) {
+                    const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                    ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * kTcBN;
+                    const uint32_t b_lo_stage = b_lo0 + stage * (stage_bytes >> 4);
+                    for (int kb = 0; kb < p.nkb; ++kb) {
+                        const int nks = p.ksteps - kb * 4;
+                        const uint32_t a_lo = a_lo0 + kb * (kTcABlockBytes >> 4);
+                        const uint32_t b_lo = b_lo_stage + kb * (kTcBHalfBytes >> 4);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            if (ks < nks)
+                                ptx::umma_bf16_ss_pair_lohi(tmem_d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc,
+                                                            (uint32_t)((kb | ks) != 0));
+                    }
+                    ptx::umma_commit_pair(&empty_bar[stage]);      // both CTAs may refill this stage
+                    ptx::umma_commit_pair(&tmem_full[as]);         // both CTAs' epilogues may read the tile
+                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit_pair(a_empty);
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + p.epi_warps) {
+        // ===== epilogue (both CTAs): own 128 query rows x 256 columns of every accumulator tile =====
+        const int ew = warp - 4;
+        const int quarter = ew & 3, half = ew >> 2, halves = p.epi_warps >> 2;
+        const int cols = kTcBN / halves;
+        const int m = quarter * 32 + lane;
+        uint32_t acc_it = 0;
+        TcRegList<KP> list;
+        for (int item = cluster_id; item < nitems; item += nclusters) {
+            const int seg = item / nqp, qt = 2 * (item % nqp) + (int)rank;
+            const int tile0 = seg * p.tiles_per_seg;
+            const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+            // seed the threshold with what earlier segments of the same query already proved: their K'-th best
+            // bounds this query's answer from below, so rows scoring under it cannot matter here either.  The slots
+            // are written by other CTAs of this launch; an unfinished one still reads -inf (memset before launch).
+            const size_t q = (size_t)qt * kTcBM + m;
+            float seed = -INFINITY;
+            for (int s2 = 0; s2 < seg; ++s2)
+                seed = fmaxf(seed, *(const volatile float*)(p.cand_thr + q * p.nslot + (size_t)s2 * halves + half));
+            list.reset(seed);
+            if (p.debug == 4) list.thr = INFINITY;       // ablation: fast path only
+            for (int t = 0; t < ntiles; ++t, ++acc_it) {
+                const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
+                const int row_base = (tile0 + t) * kTcBN + half * cols;
+                bool released = false;
+                if (p.debug != 1 && p.debug != 3) {
+                    if constexpr (KP <= 16) {
+                        // two register buffers; the accumulator stage is handed back to the MMA as soon as the last
+                        // TMEM load has landed, the last two chunks are scanned after the release
+                        float va[32], vb[32];
+                        ptx::tmem_ld_32x32(taddr, va);
+                        ptx::tmem_ld_32x32(taddr + 32, vb);
+                        for (int c = 0; c < cols; c += 64) {
+                            ptx::tmem_ld_wait();
+                            const bool last = c + 64 >= cols;
+                            if (last) {
+                                ptx::tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty[as], 0);
+                                released = true;
+                            }
+                            if (p.debug != 2) list.scan(va, row_base + c);
+                            else if (va[0] + va[31] == 12345.678f) list.thr = va[0];
+                            if (!last) ptx::tmem_ld_32x32(taddr + c + 64, va);
+                            if (p.debug != 2) list.scan(vb, row_base + c + 32);
+                            else if (vb[0] + vb[31] == 12345.678f) list.thr = vb[0];
+                            if (!last) ptx::tmem_ld_32x32(taddr + c + 96, vb);
+                        }
+                    } else {
+                        for (int c = 0; c < cols; c += 32) {
+                            float va[32];
+                            ptx::tmem_ld_32x32(taddr + c, va);
+                            ptx::tmem_ld_wait();
+                            list.scan(va, row_base + c);
+                        }
+                    }
+                }
+                if (!released) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty[as], 0);
+                }
+            }
+            const size_t slot = (size_t)seg * halves + half;
+            float* ov = p.cand_val + (q * p.nslot + slot) * KP;
+            int* oi = p.cand_idx + (q * p.nslot + slot) * KP;
+            bool full = true;
+#pragma unroll
+            for (int e = 0; e < KP; ++e) { ov[e] = list.lv[e]; oi[e] = list.lr[e]; full = full && list.lr[e] >= 0; }
+            // everything this slot dropped scores <= thr (placeholders keep thr at the seed while the list is not full)
+            p.cand_thr[q * p.nslot + slot] = (full || seed > -INFINITY) ? list.thr : -INFINITY;
+        }
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync_all();            // the peer's remote arrives / multicast commits have landed before anyone exits
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_pair(tmem_base, 512);
     }
 }
 
@@ -619,6 +846,7 @@ struct TensorState {
     TcBuffer train_bf16, center, stats, partial;
     TcBuffer q_bf16, q_norm2, q_err, cand_val, cand_idx, cand_thr, flags, fb_list, fb_count, fb_queries, fb_d, fb_i;
     CUtensorMap map_b;
+    CUtensorMap map_b_half;   // 128-row boxes for the CTA-pair kernel
     void* encode_fn = nullptr;
     int sm_count = 0;
     int smem_optin = 0;
@@ -632,6 +860,7 @@ struct TensorLaunch {
     int opt_epi_warps = 0;   // 0 = auto, else 4 or 8
     int opt_nseg = 0;        // 0 = auto
     int opt_smem_lists = 0;  // 1 = force the shared-memory list epilogue
+    int opt_cta_group = 0;   // 0 = auto, 1 = single CTA per item, 2 = CTA pairs (cta_group::2)
     int debug = 0;
 };
 
@@ -749,6 +978,8 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
     if (st.usable) {
         int rc = tc_make_map(st, &st.map_b, st.train_bf16.ptr, st.npad, st.dp, kTcBN, err);
         if (rc) return rc;
+        rc = tc_make_map(st, &st.map_b_half, st.train_bf16.ptr, st.npad, st.dp, kTcBN / 2, err);
+        if (rc) return rc;
     }
     st.ready = true;
     return 0;
@@ -766,13 +997,18 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     int epi_warps = kprime <= 32 ? 8 : 4;
     if (tl.opt_epi_warps == 4 || (tl.opt_epi_warps == 8 && (reg_lists || kprime <= 24))) epi_warps = tl.opt_epi_warps;
     const int halves = epi_warps / 4;
-    const int64_t qpad = (q + kTcBM - 1) / kTcBM * kTcBM;
+    // CTA pairs (cta_group::2) need register lists (no shared-memory list code in that kernel)
+    // (the pair kernel stages whole half-tiles; for wide rows that no longer fits twice, so use single CTAs there)
+    const size_t pair_stage = (size_t)(st.dp / kTcKB) * kTcBHalfBytes;
+    const bool pair_fits = (size_t)st.smem_optin >= (size_t)(st.dp / kTcKB) * kTcABlockBytes + 2 * pair_stage + 1280;
+    const int tc_cta_group = (reg_lists && tl.opt_cta_group != 1 && pair_fits) ? 2 : 1;
+    const int64_t qtile = (int64_t)kTcBM * tc_cta_group;
+    const int64_t qpad = (q + qtile - 1) / qtile * qtile;
     const int nqt = (int)(qpad / kTcBM);
     const int tiles_total = (int)(st.npad / kTcBN);
     const int nkb = st.dp / kTcKB;
     const int ksteps = (d + 3 + 15) / 16;
 
-    // segments: enough (query tile, segment) items to balance the persistent grid, few enough to keep K3 cheap
     // every extra segment restarts the per-query threshold (more list inserts, more candidates for K3), so use the
     // fewest that still give every SM an item; with more query tiles than SMs a single sweep per tile is best
     int max_seg_by_cand = std::max(1, kTcMaxCand / (kprime * halves));
@@ -782,8 +1018,8 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
         // 2 % per extra segment for the restarted thresholds
         double best = 1e30;
         const int units = std::max(1, st.sm_count / tc_cta_group);
-        for (int cand = 1; cand <= 8; ++cand) {
-            const double items = (double)((nqt + tc_cta_group - 1) / tc_cta_group) * cand;
+        for (int cand = 1; cand <= 32; ++cand) {
+            const double items = (double)(nqt / tc_cta_group) * cand;
             const double cost = std::ceil(items / units) / (items / units) + 0.02 * (cand - 1);
             if (cost < best - 1e-9) { best = cost; nseg = cand; }
         }
@@ -795,11 +1031,12 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     const int nslot = nseg * halves;
 
     const size_t list_bytes = reg_lists ? 0 : (size_t)kprime * epi_warps * 32 * 8;
+    const size_t stage_bytes = tc_cta_group == 2 ? (size_t)nkb * kTcBHalfBytes : (size_t)kTcBStageBytes;
     const size_t fixed = (size_t)nkb * kTcABlockBytes + list_bytes + 256 + 1024;
-    int stages = (int)(((size_t)st.smem_optin - fixed) / kTcBStageBytes);
-    stages = std::min(stages, 6);
+    int stages = (int)(((size_t)st.smem_optin - fixed) / stage_bytes);
+    stages = std::min(stages, tc_cta_group == 2 ? 8 : 6);
     if (stages < 2) { if (err) *err = "not enough shared memory for the tensor filter"; return 4; }
-    const size_t smem = (size_t)nkb * kTcABlockBytes + (size_t)stages * kTcBStageBytes + list_bytes + 256;
+    const size_t smem = (size_t)nkb * kTcABlockBytes + (size_t)stages * stage_bytes + list_bytes + 256;
 
     TC_TRY(st.q_bf16.reserve((size_t)qpad * st.dp * sizeof(__nv_bfloat16)));
     TC_TRY(st.q_norm2.reserve((size_t)qpad * sizeof(double)));
@@ -829,11 +1066,14 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     p.cand_thr = st.cand_thr.as<float>();
     p.debug = tl.debug;
     auto kernel = !reg_lists ? knn_tc_filter_kernel<0> : (kprime == 16 ? knn_tc_filter_kernel<16> : knn_tc_filter_kernel<32>);
+    if (tc_cta_group == 2) kernel = kprime == 16 ? knn_tc_filter_pair_kernel<16> : knn_tc_filter_pair_kernel<32>;
     TC_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::min(nqt * nseg, st.sm_count);
+    const int nitems = (nqt / tc_cta_group) * nseg;
+    const int grid = tc_cta_group * std::min(nitems, st.sm_count / tc_cta_group);
     if (!st.ev_k1_begin) { TC_TRY(cudaEventCreate(&st.ev_k1_begin)); TC_TRY(cudaEventCreate(&st.ev_k1_end)); }
+    TC_TRY(cudaMemsetAsync(st.cand_thr.ptr, 0xFF, (size_t)qpad * nslot * sizeof(float), stream));   // NaN bits: "not written"
     TC_TRY(cudaEventRecord(st.ev_k1_begin, stream));
-    kernel<<<grid, kTcThreads, smem, stream>>>(map_a, st.map_b, p);
+    kernel<<<grid, kTcThreads, smem, stream>>>(map_a, tc_cta_group == 2 ? st.map_b_half : st.map_b, p);
     TC_TRY(cudaEventRecord(st.ev_k1_end, stream));
     ++*launches;
     ++st.filter_launches;
