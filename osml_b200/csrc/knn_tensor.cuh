@@ -56,6 +56,8 @@ struct TcParams {
     int kprime;          // candidates kept per (query, slot)
     int epi_warps;       // 4 or 8
     int stages;          // B ring depth
+    int a_resident;      // 1: the query tile stays in shared memory for a whole sweep; 0 (wide rows): its K blocks
+                         //    are streamed through the ring next to the train blocks
     int nslot;           // nseg * halves
     float* cand_val;     // [qpad][nslot][kprime]
     int* cand_idx;
@@ -280,10 +282,12 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve: [A blocks][B ring][lists][barriers]
     unsigned char* a_smem = smem;
-    unsigned char* b_smem = a_smem + (size_t)p.nkb * kTcABlockBytes;
+    unsigned char* b_smem = a_smem + (p.a_resident ? (size_t)p.nkb * kTcABlockBytes : 0);
+    const uint32_t ring_stage_bytes = p.a_resident ? kTcBStageBytes : kTcABlockBytes + kTcBStageBytes;
+    const uint32_t ring_b_offset = p.a_resident ? 0 : kTcABlockBytes;      // streamed mode: [A block][B block]
     const int epi_threads = p.epi_warps * 32;
     const size_t list_elems = KP > 0 ? 0 : (size_t)p.kprime * epi_threads;   // register lists need no shared memory
-    float* list_val = reinterpret_cast<float*>(b_smem + (size_t)p.stages * kTcBStageBytes);
+    float* list_val = reinterpret_cast<float*>(b_smem + (size_t)p.stages * ring_stage_bytes);
     int* list_idx = reinterpret_cast<int*>(list_val + list_elems);
     uint64_t* bars = reinterpret_cast<uint64_t*>(list_idx + list_elems);
     uint64_t* full_bar = bars;                    // [stages]
@@ -322,20 +326,23 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int seg = item / p.nqt, qt = item % p.nqt;
                 const int tile0 = seg * p.tiles_per_seg;
                 const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
-                ptx::mbar_wait(a_empty, (it & 1) ^ 1);
-                ptx::mbar_expect_tx(a_full, (uint32_t)p.nkb * kTcABlockBytes);
-                for (int kb = 0; kb < p.nkb; ++kb)
-                    ptx::tma_load_2d(a_smem + (size_t)kb * kTcABlockBytes, &map_a, a_full, kb * kTcKB, qt * kTcBM);
+                if (p.a_resident) {
+                    ptx::mbar_wait(a_empty, (it & 1) ^ 1);
+                    ptx::mbar_expect_tx(a_full, (uint32_t)p.nkb * kTcABlockBytes);
+                    for (int kb = 0; kb < p.nkb; ++kb)
+                        ptx::tma_load_2d(a_smem + (size_t)kb * kTcABlockBytes, &map_a, a_full, kb * kTcKB, qt * kTcBM);
+                }
                 for (int t = 0; t < ntiles; ++t) {
                     const int row0 = (tile0 + t) * kTcBN;
                     for (int kb = 0; kb < p.nkb; ++kb) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        unsigned char* ring = b_smem + (size_t)stage * ring_stage_bytes;
                         if (p.debug == 3) {                      // ablation: no operand traffic, MMA on stale smem
                             ptx::mbar_arrive(&full_bar[stage]);
                         } else {
-                            ptx::mbar_expect_tx(&full_bar[stage], kTcBStageBytes);
-                            ptx::tma_load_2d(b_smem + (size_t)stage * kTcBStageBytes, &map_b, &full_bar[stage],
-                                             kb * kTcKB, row0);
+                            ptx::mbar_expect_tx(&full_bar[stage], ring_stage_bytes);
+                            if (!p.a_resident) ptx::tma_load_2d(ring, &map_a, &full_bar[stage], kb * kTcKB, qt * kTcBM);
+                            ptx::tma_load_2d(ring + ring_b_offset, &map_b, &full_bar[stage], kb * kTcKB, row0);
                         }
                         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                     }
@@ -353,8 +360,10 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int seg = item / p.nqt;
                 const int tile0 = seg * p.tiles_per_seg;
                 const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
-                ptx::mbar_wait(a_full, it & 1);
-                ptx::tc_fence_after();
+                if (p.a_resident) {
+                    ptx::mbar_wait(a_full, it & 1);
+                    ptx::tc_fence_after();
+                }
                 for (int t = 0; t < ntiles; ++t, ++acc_it) {
                     const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
                     ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -364,8 +373,9 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         ptx::mbar_wait(&full_bar[stage], phase);
                         ptx::tc_fence_after();
                         const int nks = p.ksteps - kb * 4;
-                        const uint32_t a_lo = a_lo0 + kb * (kTcABlockBytes >> 4);
-                        const uint32_t b_lo = b_lo0 + stage * (kTcBStageBytes >> 4);
+                        const uint32_t ring_lo = b_lo0 + stage * (ring_stage_bytes >> 4);
+                        const uint32_t a_lo = p.a_resident ? a_lo0 + kb * (kTcABlockBytes >> 4) : ring_lo;
+                        const uint32_t b_lo = ring_lo + (ring_b_offset >> 4);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
                             if (ks < nks)
@@ -376,7 +386,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     }
                     ptx::umma_commit(&tmem_full[as]);              // accumulator tile ready for the epilogue
                 }
-                ptx::umma_commit(a_empty);                         // query tile may be overwritten
+                if (p.a_resident) ptx::umma_commit(a_empty);       // query tile may be overwritten
             }
         }
     } else if (warp >= 4 && warp < 4 + p.epi_warps) {
@@ -868,19 +878,22 @@ using DirectFallback = std::function<int(const void*, int64_t, void*, int64_t*)>
 
 inline int tc_default_slack(int k) { return std::max(5, (k + 1) / 3); }
 
+// List length per (query, slot).  With register lists two epilogue threads share a query row (one per column half), so
+// a segment keeps 2 * K' candidates; each half must still be able to hold its share of the true k+1 nearest, which is
+// Binomial(k+1, 1/2): K' >= (k+1)/2 + 2*sqrt(k+1) keeps the overflow probability below 1e-4.
 inline int tc_kprime(int k, int slack) {
     if (slack < 0) slack = tc_default_slack(k);
-    int kp = k + 1 + slack;
-    if (kp <= 16) return 16;        // register-resident lists come in 16 and 32 entries
-    if (kp <= 32) return 32;
-    return (kp + 7) / 8 * 8;        // shared-memory lists
+    const int need = k + 1 + slack;
+    const double half_share = 0.5 * (k + 1) + 2.0 * std::sqrt((double)(k + 1));
+    if (need <= 32 && half_share <= 16.0) return 16;      // register lists, 16 per half
+    if (need <= 64 && half_share <= 32.0) return 32;      // register lists, 32 per half
+    return (need + 7) / 8 * 8;                            // shared-memory lists, one thread per query row
 }
 
 inline bool tensor_path_supported(int dtype, int64_t n, int64_t d, int k) {
     if (dtype != 0 /* OSML_KNN_F32 */) return false;
     if (n < 256 || d < 1) return false;
-    const int64_t dp = (d + 3 + kTcKB - 1) / kTcKB * kTcKB;
-    if (dp / kTcKB > 5) return false;             // query tile must stay resident in shared memory (d <= 317)
+    if (d > 8189) return false;                   // 128 K blocks of 64 bf16
     return tc_kprime(k, -1) <= kTcMaxKPrime;
 }
 
@@ -994,7 +1007,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     const int kprime = tc_kprime(tl.k, tl.slack);
     if (kprime > kTcMaxKPrime) { if (err) *err = "k + 1 + slack exceeds 64"; return 4; }
     const bool reg_lists = kprime <= 32 && !tl.opt_smem_lists;
-    int epi_warps = kprime <= 32 ? 8 : 4;
+    int epi_warps = reg_lists ? 8 : 4;
     if (tl.opt_epi_warps == 4 || (tl.opt_epi_warps == 8 && (reg_lists || kprime <= 24))) epi_warps = tl.opt_epi_warps;
     const int halves = epi_warps / 4;
     // CTA pairs (cta_group::2) need register lists (no shared-memory list code in that kernel)
@@ -1031,12 +1044,17 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     const int nslot = nseg * halves;
 
     const size_t list_bytes = reg_lists ? 0 : (size_t)kprime * epi_warps * 32 * 8;
-    const size_t stage_bytes = tc_cta_group == 2 ? (size_t)nkb * kTcBHalfBytes : (size_t)kTcBStageBytes;
-    const size_t fixed = (size_t)nkb * kTcABlockBytes + list_bytes + 256 + 1024;
+    // the query tile stays resident when it leaves room for at least two ring stages; wide rows stream it instead
+    const bool a_resident = tc_cta_group == 2 ||
+        (size_t)st.smem_optin >= (size_t)nkb * kTcABlockBytes + list_bytes + 2 * (size_t)kTcBStageBytes + 1280;
+    const size_t a_bytes = a_resident ? (size_t)nkb * kTcABlockBytes : 0;
+    const size_t stage_bytes = tc_cta_group == 2 ? (size_t)nkb * kTcBHalfBytes
+                               : (a_resident ? (size_t)kTcBStageBytes : (size_t)kTcABlockBytes + kTcBStageBytes);
+    const size_t fixed = a_bytes + list_bytes + 256 + 1024;
     int stages = (int)(((size_t)st.smem_optin - fixed) / stage_bytes);
     stages = std::min(stages, tc_cta_group == 2 ? 8 : 6);
     if (stages < 2) { if (err) *err = "not enough shared memory for the tensor filter"; return 4; }
-    const size_t smem = (size_t)nkb * kTcABlockBytes + (size_t)stages * stage_bytes + list_bytes + 256;
+    const size_t smem = a_bytes + (size_t)stages * stage_bytes + list_bytes + 256;
 
     TC_TRY(st.q_bf16.reserve((size_t)qpad * st.dp * sizeof(__nv_bfloat16)));
     TC_TRY(st.q_norm2.reserve((size_t)qpad * sizeof(double)));
@@ -1061,7 +1079,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
 
     TcParams p;
     p.nkb = nkb; p.ksteps = ksteps; p.nqt = nqt; p.nseg = nseg; p.tiles_per_seg = tiles_per_seg;
-    p.tiles_total = tiles_total; p.kprime = kprime; p.epi_warps = epi_warps; p.stages = stages; p.nslot = nslot;
+    p.tiles_total = tiles_total; p.kprime = kprime; p.epi_warps = epi_warps; p.stages = stages; p.nslot = nslot; p.a_resident = a_resident ? 1 : 0;
     p.cand_val = st.cand_val.as<float>(); p.cand_idx = st.cand_idx.as<int>();
     p.cand_thr = st.cand_thr.as<float>();
     p.debug = tl.debug;

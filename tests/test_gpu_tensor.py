@@ -103,3 +103,28 @@ def test_nonfinite_queries_and_train_rows():
     train2[100, 7] = np.inf
     pred, idx, dist, stats = _run(train2, labels, test, 7)
     parity.assert_matches_oracle(pred, idx, dist, train2, labels, test, 7, 1, 'classification')
+
+
+def test_wide_rows_stream_the_query_tile():
+    """MNIST-shaped rows (BASELINE config 3: d = 784): the query tile no longer fits in shared memory next to the ring,
+    so its K blocks are streamed with the train blocks."""
+    rng = np.random.default_rng(14)
+    n, d, q, k = 6000, 784, 300, 10
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = rng.standard_normal((q, d), dtype=np.float32)
+    labels = rng.integers(0, 10, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+    assert stats['fallback_queries'] <= q // 20, stats
+
+
+@pytest.mark.parametrize('k', [14, 15, 20, 37, 38, 45])
+def test_list_length_plans(k):
+    """k decides between 16- and 32-entry register lists and the shared-memory lists."""
+    rng = np.random.default_rng(100 + k)
+    train = np.asfortranarray(rng.standard_normal((9000, 24), dtype=np.float32))
+    test = rng.standard_normal((200, 24), dtype=np.float32)
+    labels = rng.standard_normal(9000)
+    pred, idx, dist, stats = _run(train, labels, test, k, task='regression')
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'regression')
+    assert stats['fallback_queries'] <= 20, stats
