@@ -739,12 +739,37 @@ struct TcBounds {
 
 constexpr int kRescoreWarps = 4;
 
+// exact fp32 distance, 16-byte loads when the row length allows (same left-to-right order as sum_sequential)
+__device__ __forceinline__ float tc_exact_distance(const float* __restrict__ t, const float* __restrict__ q, int d,
+                                                   int sum_order) {
+    if (sum_order == 1 && (d & 3) == 0) {
+        using E = Elem<float>;
+        const float4* t4 = reinterpret_cast<const float4*>(t);
+        const float4* q4 = reinterpret_cast<const float4*>(q);
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int j = 0; j < d / 4; ++j) {
+            const float4 a = __ldg(t4 + j), b = __ldg(q4 + j);
+            acc = E::add(acc, E::sq_diff(a.x, b.x));
+            acc = E::add(acc, E::sq_diff(a.y, b.y));
+            acc = E::add(acc, E::sq_diff(a.z, b.z));
+            acc = E::add(acc, E::sq_diff(a.w, b.w));
+        }
+        return E::finish(acc);
+    }
+    return exact_distance<float>(t, q, d, sum_order);
+}
+
+// One warp per query.  Exact distances are only computed where they can matter: first for the k+1 candidates with the
+// best filter score, whose largest exact distance D0 caps the answer; any other candidate whose score-derived lower
+// bound already exceeds D0 cannot be among the k+1 nearest and is never gathered from HBM.
 __global__ void __launch_bounds__(32 * kRescoreWarps)
 knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __restrict__ queries, int d, int sum_order,
                    int64_t q_count, int ksel, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
-                   const float* __restrict__ cand_thr, int nslot, int kprime, const double* __restrict__ qnorm2, const double* __restrict__ qerr,
-                   TcBounds bounds, int64_t index_base, float* __restrict__ out_d, int64_t* __restrict__ out_i,
-                   int* __restrict__ flags) {
+                   const float* __restrict__ cand_thr, int nslot, int kprime, const double* __restrict__ qnorm2,
+                   const double* __restrict__ qerr, TcBounds bounds, int64_t index_base, float* __restrict__ out_d,
+                   int64_t* __restrict__ out_i, int* __restrict__ flags) {
+    __shared__ float s_acc[kRescoreWarps][kTcMaxCand];
     __shared__ float s_dist[kRescoreWarps][kTcMaxCand];
     __shared__ int s_idx[kRescoreWarps][kTcMaxCand];
     __shared__ float s_best[kRescoreWarps];
@@ -752,52 +777,85 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
     const int64_t q = (int64_t)blockIdx.x * kRescoreWarps + warp;
     if (q >= q_count) return;
     const int ncand = nslot * kprime;
+    const float* cv = cand_val + (size_t)q * ncand;
     const int* ci = cand_idx + (size_t)q * ncand;
     const float* qrow = queries + (size_t)q * d;
+    float* acc = s_acc[warp];
     float* dist = s_dist[warp];
     int* idx = s_idx[warp];
 
+    const double n2 = qnorm2[q], eq = qerr[q];
+    const double eps = bounds.c_mma * (sqrt(n2) * bounds.tnorm_max + 0.5 * bounds.tnorm_max * bounds.tnorm_max);
+    // every row whose filter score is <= a has an exact (oracle-arithmetic) distance >= lower(a)
+    auto lower = [&](float a) {
+        const double l2 = n2 - 2.0 * ((double)a + eps);
+        return (sqrt(fmax(l2, 0.0)) - (eq + bounds.et_max)) * (1.0 - bounds.gamma);
+    };
+
+    int nvalid = 0;
     for (int c = lane; c < ncand; c += 32) {
         const int row = ci[c];
-        if (row >= 0 && row < n) {        // negative: empty slot; >= n: a padding row of the filter copy
-            dist[c] = exact_distance<float>(train + (size_t)row * d, qrow, d, sum_order);
-            idx[c] = row;
-        } else {
-            dist[c] = nan_of<float>();
-            idx[c] = kIdxSentinel;
+        const bool valid = row >= 0 && row < n;       // negative: empty slot; >= n: a padding row of the filter copy
+        idx[c] = valid ? row : kIdxSentinel;
+        acc[c] = valid ? cv[c] : -INFINITY;
+        dist[c] = nan_of<float>();                    // "not computed": sorts after everything
+        nvalid += valid ? 1 : 0;
+    }
+    for (int off = 16; off > 0; off >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, off);
+    __syncwarp();
+    bool ok = nvalid >= ksel;
+    // pass 1: the k+1 best-scoring candidates (selection first, then the gathers, so ranks see a stable score array)
+    uint32_t selected = 0;                            // bit i: candidate lane + 32 * i
+    for (int c = lane, i = 0; c < ncand; c += 32, ++i) {
+        if (idx[c] == kIdxSentinel) continue;
+        const float ac = acc[c];
+        int rank = 0;
+        for (int o = 0; o < ncand; ++o) {
+            const float ao = acc[o];
+            rank += (ao > ac || (ao == ac && o < c)) ? 1 : 0;
         }
+        if (rank < ksel) selected |= 1u << i;
+    }
+    float d0 = 0.0f;
+    bool d0_nan = false;
+    for (int c = lane, i = 0; c < ncand; c += 32, ++i) {
+        if (!((selected >> i) & 1u)) continue;
+        const float dc = tc_exact_distance(train + (size_t)idx[c] * d, qrow, d, sum_order);
+        dist[c] = dc;
+        d0 = fmaxf(d0, dc);
+        d0_nan = d0_nan || dc != dc;
+    }
+    for (int off = 16; off > 0; off >>= 1) d0 = fmaxf(d0, __shfl_xor_sync(0xffffffffu, d0, off));
+    d0_nan = __any_sync(0xffffffffu, d0_nan) || !ok;
+    const double cap = d0_nan ? (double)INFINITY : (double)d0 * (1.0 + 9.5367431640625e-07);
+    __syncwarp();
+    // pass 2: whatever the cap cannot rule out
+    for (int c = lane; c < ncand; c += 32) {
+        if (idx[c] == kIdxSentinel || dist[c] == dist[c]) continue;         // empty, or already computed in pass 1
+        if (lower(acc[c]) > cap) { idx[c] = kIdxSentinel; continue; }       // provably beyond the (k+1)-th nearest
+        dist[c] = tc_exact_distance(train + (size_t)idx[c] * d, qrow, d, sum_order);
     }
     __syncwarp();
-    // rank by (distance, index); keys are unique because the slots cover disjoint row ranges
-    int nvalid_local = 0;
+    // rank the computed candidates by (distance, index); keys are unique because the slots cover disjoint row ranges
     for (int c = lane; c < ncand; c += 32) {
         const int ic = idx[c];
         if (ic == kIdxSentinel) continue;
-        ++nvalid_local;
         const float dc = dist[c];
         int rank = 0;
-        for (int o = 0; o < ncand; ++o) rank += key_less(dist[o], idx[o], dc, ic) ? 1 : 0;
+        for (int o = 0; o < ncand; ++o) rank += (idx[o] != kIdxSentinel && key_less(dist[o], idx[o], dc, ic)) ? 1 : 0;
         if (rank < ksel) {
             out_d[q * ksel + rank] = dc;
             out_i[q * ksel + rank] = index_base + ic;
             if (rank == ksel - 1) s_best[warp] = dc;
         }
     }
-    int nvalid = nvalid_local;
-    for (int off = 16; off > 0; off >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, off);
     __syncwarp();
-    bool ok = nvalid >= ksel;
     if (ok) {
         const double dk = (double)s_best[warp] * (1.0 + 9.5367431640625e-07);   // (k+1)-th exact distance, 2^-20 margin
-        const double n2 = qnorm2[q], eq = qerr[q];
-        const double qn = sqrt(n2);
-        const double eps = bounds.c_mma * (qn * bounds.tnorm_max + 0.5 * bounds.tnorm_max * bounds.tnorm_max);
         for (int s = lane; s < nslot; s += 32) {
             const float thr = cand_thr[(size_t)q * nslot + s];
             if (thr == -INFINITY) continue;   // the slot never filled its list: nothing was dropped
-            const double l2 = n2 - 2.0 * ((double)thr + eps);
-            const double lower = (sqrt(fmax(l2, 0.0)) - (eq + bounds.et_max)) * (1.0 - bounds.gamma);
-            if (!(lower > dk)) ok = false;    // also catches NaN
+            if (!(lower(thr) > dk)) ok = false;    // also catches NaN
         }
     }
     ok = __all_sync(0xffffffffu, ok);
@@ -1028,12 +1086,12 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     int nseg = 1;
     {
         // work items = nqt * nseg over sm_count persistent CTAs: pick the split with the least idle tail, charging
-        // 2 % per extra segment for the restarted thresholds
+        // 1 % per extra segment (later segments start from the thresholds earlier ones proved, so they are cheap)
         double best = 1e30;
         const int units = std::max(1, st.sm_count / tc_cta_group);
         for (int cand = 1; cand <= 32; ++cand) {
             const double items = (double)(nqt / tc_cta_group) * cand;
-            const double cost = std::ceil(items / units) / (items / units) + 0.02 * (cand - 1);
+            const double cost = std::ceil(items / units) / (items / units) + 0.01 * (cand - 1);
             if (cost < best - 1e-9) { best = cost; nseg = cand; }
         }
     }
