@@ -184,22 +184,26 @@ int convert_labels(const void* labels, int label_dtype, int64_t n, std::vector<i
 // ---------------------------------------------------------------------------------------------------------------------
 // K2 launch
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename T, int TN, int DCH>
+template <typename T>
 int launch_direct_typed(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d, int64_t* out_i,
                         cudaStream_t stream) {
     using Dist = typename osml::Elem<T>::Dist;
     const int ksel = ix->ksel();
     const int n = (int)ix->n, d = (int)ix->d;
-    const int ctas_q = (int)((q + osml::kDirectQT - 1) / osml::kDirectQT);
     const bool generic = osml::Elem<T>::kIsFloat && ix->sum_order == OSML_KNN_SUM_PAIRWISE && d > 1;
+    const int qgroup = generic ? osml::kDirectQT : osml::kRowQB;
+    const int ctas_q = (int)((q + qgroup - 1) / qgroup);
+    // split the train rows until the grid covers the machine a few times over
+    const int row_quant = generic ? 64 : osml::kRowThreads;
     int nsplit = 1;
-    if (ctas_q < 296) {
-        nsplit = (296 + ctas_q - 1) / ctas_q;
-        const int max_split = std::max(1, n / (4 * TN));
+    const int target_ctas = generic ? 296 : 148 * 8;
+    if (ctas_q < target_ctas) {
+        nsplit = (target_ctas + ctas_q - 1) / ctas_q;
+        const int max_split = std::max(1, n / (2 * row_quant));
         nsplit = std::max(1, std::min(std::min(nsplit, 64), max_split));
     }
     int rows_per_split = (n + nsplit - 1) / nsplit;
-    rows_per_split = ((rows_per_split + TN - 1) / TN) * TN;
+    rows_per_split = ((rows_per_split + row_quant - 1) / row_quant) * row_quant;
     nsplit = (n + rows_per_split - 1) / rows_per_split;
 
     Dist* part_d = static_cast<Dist*>(out_d);
@@ -219,11 +223,14 @@ int launch_direct_typed(osml_knn_index* ix, const void* d_queries, int64_t q, vo
                                                       ksel, rows_per_split, ix->index_base, ix->sum_order, part_d,
                                                       part_i);
     } else {
-        const size_t smem = osml::DirectSmem<T, TN, DCH>::bytes(ksel);
-        auto kern = osml::knn_direct_seq_kernel<T, TN, DCH>;
+        const size_t smem = osml::RowSmem<T>::bytes(d, ksel);
+        if (smem > 200 * 1024) return fail(OSML_KNN_EUNSUPPORTED, "row too long for the direct kernel's query tile");
+        // 16-byte row loads need 16-byte aligned rows (the base comes from cudaMalloc)
+        const bool vec = ((size_t)d * sizeof(T)) % 16 == 0;
+        auto kern = vec ? osml::knn_direct_rows_kernel<T, true> : osml::knn_direct_rows_kernel<T, false>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, osml::kDirectQT, smem, stream>>>(ix->train.as<T>(), static_cast<const T*>(d_queries), n, d, (int)q,
-                                                      ksel, rows_per_split, ix->index_base, part_d, part_i);
+        kern<<<grid, osml::kRowThreads, smem, stream>>>(ix->train.as<T>(), static_cast<const T*>(d_queries), n, d,
+                                                        (int)q, ksel, rows_per_split, ix->index_base, part_d, part_i);
     }
     ix->stats.kernel_launches++;
     ix->stats.last_filter_launches++;
@@ -241,16 +248,16 @@ int launch_direct_typed(osml_knn_index* ix, const void* d_queries, int64_t q, vo
 int launch_direct(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d, int64_t* out_i,
                   cudaStream_t stream) {
     switch (ix->dtype) {
-        case OSML_KNN_F32: return launch_direct_typed<float, 32, 16>(ix, d_queries, q, out_d, out_i, stream);
-        case OSML_KNN_F64: return launch_direct_typed<double, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
-        case OSML_KNN_I8: return launch_direct_typed<int8_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
-        case OSML_KNN_I16: return launch_direct_typed<int16_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
-        case OSML_KNN_I32: return launch_direct_typed<int32_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
-        case OSML_KNN_I64: return launch_direct_typed<int64_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
-        case OSML_KNN_U8: return launch_direct_typed<uint8_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
-        case OSML_KNN_U16: return launch_direct_typed<uint16_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
-        case OSML_KNN_U32: return launch_direct_typed<uint32_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
-        case OSML_KNN_U64: return launch_direct_typed<uint64_t, 16, 16>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_F32: return launch_direct_typed<float>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_F64: return launch_direct_typed<double>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_I8: return launch_direct_typed<int8_t>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_I16: return launch_direct_typed<int16_t>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_I32: return launch_direct_typed<int32_t>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_I64: return launch_direct_typed<int64_t>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_U8: return launch_direct_typed<uint8_t>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_U16: return launch_direct_typed<uint16_t>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_U32: return launch_direct_typed<uint32_t>(ix, d_queries, q, out_d, out_i, stream);
+        case OSML_KNN_U64: return launch_direct_typed<uint64_t>(ix, d_queries, q, out_d, out_i, stream);
         default: return fail(OSML_KNN_EUNSUPPORTED, "unsupported dtype");
     }
 }

@@ -1,16 +1,11 @@
-// K2: exact direct-difference distance kernel with a fused per-query top-(k+1) selection.
+// K2: exact direct-difference distance kernels with a fused per-query top-(k+1) selection.
 //
-// Replaces predict.py:742 (_distances) + predict.py:750 (argpartition) for every dtype the reference accepts, in the
+// Replace predict.py:742 (_distances) + predict.py:750 (argpartition) for every dtype the reference accepts, in the
 // reference's own arithmetic (Elem<T>) and summation order, so distances are bit-identical to numpy's and the
-// neighbour order is the documented (distance, index) rule.  The N x Q distance matrix is never written: each
-// thread owns one query, keeps its running list in shared memory and only touches it for the rare candidate that
-// beats its current (k+1)-th best.
-//
-// Tiling (sequential order): a CTA holds QT=128 queries (one per thread) and walks the train rows in tiles of TN rows;
-// features are staged through shared memory DCH at a time (train chunk row-major, read as warp-wide broadcasts; query
-// chunk transposed so thread t reads column t conflict-free).  Each thread carries TN accumulators in registers, so
-// one broadcast LDS feeds 3 arithmetic instructions per (row, feature) -- the minimum the un-fused
-// subtract/multiply/add of the oracle allows.
+// neighbour order is the documented (distance, index) rule.  The N x Q distance matrix is never written.
+//   knn_direct_rows_kernel     sequential summation order (F-ordered DataFrame.values, and all integer dtypes)
+//   knn_direct_generic_kernel  numpy's pairwise order (C-ordered float matrices; pandas >= 3 never produces them)
+//   knn_merge_lists_kernel     exact merge of partial lists (row splits here, GPU shards in the train-sharded mode)
 #pragma once
 #include "knn_common.cuh"
 
@@ -40,102 +35,126 @@ struct TopList {
     }
 };
 
-template <typename T, int TN, int DCH>
-struct DirectSmem {
-    static constexpr int kQPitch = kDirectQT + (sizeof(T) >= 4 ? 1 : 4 / sizeof(T));
-    static size_t bytes(int ksel) {
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-parallel exact kernel (sequential summation order, every dtype).
+//
+// A CTA of 256 threads serves QB = 8 queries and a contiguous range of train rows.  Thread t owns one train row per
+// batch of 256 rows and accumulates its distance to all 8 queries at once: per feature one (vectorised) load of its own
+// row element, the 8 query values as broadcast shared-memory reads, and 8 x (subtract, multiply, add) -- the three
+// un-fusable instructions per element that numpy parity dictates.  Train rows are read straight from global memory
+// (each thread walks its own row; consecutive threads take consecutive rows, so a warp streams one contiguous 32-row
+// block through L1).
+//
+// Selection: a distance that beats the query's current (k+1)-th best is appended to that query's shared-memory buffer
+// (one atomicAdd); after each batch warp w folds buffer w into the sorted list of query w and refreshes its threshold.
+// Partial lists per (query, row split) are merged by knn_merge_lists_kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kRowQB = 8;          // queries per CTA (= warps per CTA)
+constexpr int kRowThreads = 256;
+
+template <typename T>
+struct RowSmem {
+    using Dist = typename Elem<T>::Dist;
+    static size_t bytes(int d, int ksel) {
         size_t b = 0;
-        b += (size_t)ksel * kDirectQT * sizeof(typename Elem<T>::Dist);
-        b += (size_t)ksel * kDirectQT * sizeof(int);
-        b += (size_t)TN * DCH * sizeof(T);
-        b += (size_t)DCH * kQPitch * sizeof(T);
-        return b + 16;
+        b += ((size_t)d * kRowQB * sizeof(T) + 15) / 16 * 16;                 // query tile, [feature][query]
+        b += (size_t)kRowQB * kRowThreads * (sizeof(Dist) + sizeof(int));     // candidate buffers
+        b += (size_t)kRowQB * ksel * (sizeof(Dist) + sizeof(int));            // sorted lists
+        return b + 64;
     }
 };
 
-// sum_order == sequential (or integer data): register-tiled kernel
-template <typename T, int TN, int DCH>
-__global__ void __launch_bounds__(kDirectQT)
-knn_direct_seq_kernel(const T* __restrict__ train, const T* __restrict__ queries, int n, int d, int q_count, int ksel,
-                      int rows_per_split, int64_t index_base,
-                      typename Elem<T>::Dist* __restrict__ part_d, int64_t* __restrict__ part_i) {
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kRowThreads)
+knn_direct_rows_kernel(const T* __restrict__ train, const T* __restrict__ queries, int n, int d, int q_count, int ksel,
+                       int rows_per_split, int64_t index_base, typename Elem<T>::Dist* __restrict__ part_d,
+                       int64_t* __restrict__ part_i) {
     using E = Elem<T>;
     using Acc = typename E::Acc;
     using Dist = typename E::Dist;
-    constexpr int kQPitch = DirectSmem<T, TN, DCH>::kQPitch;
+    constexpr int kVecElems = kVec ? (int)(16 / sizeof(T)) : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Dist* list_d = reinterpret_cast<Dist*>(smem_raw);
-    int* list_i = reinterpret_cast<int*>(list_d + (size_t)ksel * kDirectQT);
-    T* t_s = reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(list_i + (size_t)ksel * kDirectQT + 3) & ~(uintptr_t)15);
-    T* q_s = t_s + TN * DCH;
+    T* q_s = reinterpret_cast<T*>(smem_raw);                                              // [d][kRowQB]
+    const size_t q_bytes = ((size_t)d * kRowQB * sizeof(T) + 15) / 16 * 16;
+    Dist* buf_d = reinterpret_cast<Dist*>(smem_raw + q_bytes);                            // [kRowQB][kRowThreads]
+    Dist* list_d = buf_d + kRowQB * kRowThreads;                                          // [kRowQB][ksel]
+    int* buf_i = reinterpret_cast<int*>(list_d + kRowQB * ksel);                          // [kRowQB][kRowThreads]
+    int* list_i = buf_i + kRowQB * kRowThreads;                                           // [kRowQB][ksel]
+    __shared__ int s_cnt[kRowQB];
+    __shared__ Acc s_thr[kRowQB];
 
-    const int tid = threadIdx.x;
-    const int q0 = blockIdx.x * kDirectQT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * kRowQB;
     const int split = blockIdx.y, nsplit = gridDim.y;
     const int n_begin = min(n, split * rows_per_split);
     const int n_end = min(n, n_begin + rows_per_split);
-    const bool q_valid = q0 + tid < q_count;
-    const bool single_chunk = d <= DCH;
 
-    TopList<Dist> list;
-    list.init(list_d, list_i, ksel, tid);
-    Dist wd = nan_of<Dist>();
-    int wi = kIdxSentinel;
-    Acc thr = E::threshold(wd);
-
-    for (int row0 = n_begin; row0 < n_end; row0 += TN) {
-        Acc acc[TN];
-#pragma unroll
-        for (int r = 0; r < TN; ++r) acc[r] = (Acc)0;
-        for (int j0 = 0; j0 < d; j0 += DCH) {
-            __syncthreads();
-            // train chunk: TN x DCH, zero padded
-            for (int e = tid; e < TN * DCH; e += kDirectQT) {
-                const int r = e / DCH, jj = e % DCH;
-                const int row = row0 + r, j = j0 + jj;
-                T v = (T)0;
-                if (row < n_end && j < d) v = train[(size_t)row * d + j];
-                t_s[e] = v;
-            }
-            if (!single_chunk || row0 == n_begin) {
-                for (int e = tid; e < kDirectQT * DCH; e += kDirectQT) {
-                    const int qi = e / DCH, jj = e % DCH;
-                    const int qq = q0 + qi, j = j0 + jj;
-                    T v = (T)0;
-                    if (qq < q_count && j < d) v = queries[(size_t)qq * d + j];
-                    q_s[jj * kQPitch + qi] = v;
-                }
-            }
-            __syncthreads();
-            T qreg[DCH];
-#pragma unroll
-            for (int jj = 0; jj < DCH; ++jj) qreg[jj] = q_s[jj * kQPitch + tid];
-#pragma unroll
-            for (int r = 0; r < TN; ++r) {
-#pragma unroll
-                for (int jj = 0; jj < DCH; ++jj) acc[r] = E::add(acc[r], E::sq_diff(t_s[r * DCH + jj], qreg[jj]));
-            }
-        }
-        if (q_valid) {
-#pragma unroll
-            for (int r = 0; r < TN; ++r) {
-                const int row = row0 + r;
-                if (row < n_end && E::may_beat(acc[r], thr)) {
-                    const Dist dc = E::finish(acc[r]);
-                    if (key_less(dc, row, wd, wi)) {
-                        list.insert(dc, row);
-                        wd = list.worst_d(); wi = list.worst_i();
-                        thr = E::threshold(wd);
-                    }
-                }
-            }
-        }
+    for (int e = tid; e < d * kRowQB; e += kRowThreads) {
+        const int j = e / kRowQB, qi = e % kRowQB;
+        q_s[e] = (q0 + qi < q_count) ? queries[(size_t)(q0 + qi) * d + j] : (T)0;
     }
-    if (q_valid) {
-        const size_t base = ((size_t)(q0 + tid) * nsplit + split) * ksel;
-        for (int e = 0; e < ksel; ++e) {
-            const int li = list.i[e * kDirectQT];
-            part_d[base + e] = list.d[e * kDirectQT];
+    for (int e = lane; e < ksel; e += 32) { list_d[warp * ksel + e] = nan_of<Dist>(); list_i[warp * ksel + e] = kIdxSentinel; }
+    if (tid < kRowQB) { s_cnt[tid] = 0; s_thr[tid] = E::threshold(nan_of<Dist>()); }
+    __syncthreads();
+
+    for (int row0 = n_begin; row0 < n_end; row0 += kRowThreads) {
+        const int row = row0 + tid;
+        if (row < n_end) {
+            const T* __restrict__ trow = train + (size_t)row * d;
+            Acc acc[kRowQB];
+#pragma unroll
+            for (int qi = 0; qi < kRowQB; ++qi) acc[qi] = (Acc)0;
+            for (int j0 = 0; j0 < d; j0 += kVecElems) {
+                T tv[kVecElems];
+                if (kVec) {
+                    const int4 raw = __ldg(reinterpret_cast<const int4*>(trow + j0));
+                    *reinterpret_cast<int4*>(tv) = raw;
+                } else {
+                    tv[0] = trow[j0];
+                }
+#pragma unroll
+                for (int jj = 0; jj < kVecElems; ++jj) {
+                    const T* qv = q_s + (size_t)(j0 + jj) * kRowQB;
+#pragma unroll
+                    for (int qi = 0; qi < kRowQB; ++qi) acc[qi] = E::add(acc[qi], E::sq_diff(tv[jj], qv[qi]));
+                }
+            }
+#pragma unroll
+            for (int qi = 0; qi < kRowQB; ++qi) {
+                if (E::may_beat(acc[qi], s_thr[qi])) {
+                    const int slot = atomicAdd(&s_cnt[qi], 1);
+                    buf_d[qi * kRowThreads + slot] = E::finish(acc[qi]);
+                    buf_i[qi * kRowThreads + slot] = row;
+                }
+            }
+        }
+        __syncthreads();
+        // warp w folds the candidates of query w into its sorted list (lane 0; after warm-up the buffer is almost empty)
+        const int cnt = s_cnt[warp];
+        if (cnt > 0 && lane == 0) {
+            Dist* ld = list_d + warp * ksel;
+            int* li = list_i + warp * ksel;
+            for (int c = 0; c < cnt; ++c) {
+                const Dist dc = buf_d[warp * kRowThreads + c];
+                const int ic = buf_i[warp * kRowThreads + c];
+                if (!key_less(dc, ic, ld[ksel - 1], li[ksel - 1])) continue;
+                int pos = ksel - 1;
+                while (pos > 0 && key_less(dc, ic, ld[pos - 1], li[pos - 1])) {
+                    ld[pos] = ld[pos - 1]; li[pos] = li[pos - 1];
+                    --pos;
+                }
+                ld[pos] = dc; li[pos] = ic;
+            }
+            s_thr[warp] = E::threshold(ld[ksel - 1]);
+            s_cnt[warp] = 0;
+        }
+        __syncthreads();
+    }
+    if (q0 + warp < q_count) {
+        const size_t base = ((size_t)(q0 + warp) * nsplit + split) * ksel;
+        for (int e = lane; e < ksel; e += 32) {
+            const int li = list_i[warp * ksel + e];
+            part_d[base + e] = list_d[warp * ksel + e];
             part_i[base + e] = li == kIdxSentinel ? kIdxSentinel64 : index_base + li;
         }
     }
