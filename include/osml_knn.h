@@ -73,6 +73,8 @@ typedef struct osml_knn_stats {
     double last_total_ms;        /* device time of the whole last predict call (CUDA events) */
     int64_t last_filter_launches;
     int64_t device_bytes;        /* device memory held by the handle */
+    int64_t retry_queries;       /* queries K3 could not prove on the first filter pass and that went through the
+                                    finer-grained second filter pass (those it still cannot prove count as fallback) */
 } osml_knn_stats;
 
 /*

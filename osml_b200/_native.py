@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libosml_knn.so')
+# OSML_KNN_LIB: development override for A/B timing of two builds of the same library (tools/ab.sh)
+LIB_PATH = os.environ.get('OSML_KNN_LIB') or os.path.join(_HERE, 'libosml_knn.so')
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4
 ROW_MAJOR, COL_MAJOR = 0, 1
@@ -35,7 +36,8 @@ class Stats(ctypes.Structure):
     _fields_ = [('kernel_launches', ctypes.c_int64), ('queries', ctypes.c_int64),
                 ('fallback_queries', ctypes.c_int64), ('tensor_queries', ctypes.c_int64),
                 ('last_filter_ms', ctypes.c_double), ('last_total_ms', ctypes.c_double),
-                ('last_filter_launches', ctypes.c_int64), ('device_bytes', ctypes.c_int64)]
+                ('last_filter_launches', ctypes.c_int64), ('device_bytes', ctypes.c_int64),
+                ('retry_queries', ctypes.c_int64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

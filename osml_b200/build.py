@@ -32,19 +32,22 @@ def _stale():
     return any(os.path.getmtime(p) > built for p in deps)
 
 
-def build(force=False, verbose=False):
-    """Compiles every CUDA source of the package into libosml_knn.so; returns the path."""
-    if not force and not _stale():
+def build(force=False, verbose=False, out=OUT, defines=()):
+    """Compiles every CUDA source of the package into libosml_knn.so; returns the path.
+    `out` / `defines` build experimental variants for A/B timing (tools/ab.sh); the product is the default build."""
+    if not force and out == OUT and not _stale():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else [])
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ['-o', OUT]
+    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-D' + d for d in defines]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ['-o', out]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed (%d): %s' % (res.returncode, ' '.join(cmd)))
-    return OUT
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    _defs = [a[2:] for a in sys.argv if a.startswith('-D')]
+    _out = [a[6:] for a in sys.argv if a.startswith('--out=')]
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, out=_out[0] if _out else OUT, defines=_defs))

@@ -96,6 +96,7 @@ struct osml_knn_index {
     int opt_smem_lists = 0;
     int opt_cta_group = 0;
     int debug = 0;
+    int counters = 0;
     int64_t query_block = 0;
 
     DeviceBuffer train;        // row-major n x d, original dtype
@@ -280,7 +281,7 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         osml::TensorLaunch tl;
         tl.train = ix->train.ptr; tl.dtype = ix->dtype; tl.n = ix->n; tl.d = ix->d; tl.k = ix->k;
         tl.sum_order = ix->sum_order; tl.index_base = ix->index_base; tl.slack = ix->slack;
-        tl.opt_epi_warps = ix->opt_epi_warps; tl.opt_nseg = ix->opt_nseg; tl.debug = ix->debug;
+        tl.opt_epi_warps = ix->opt_epi_warps; tl.opt_nseg = ix->opt_nseg; tl.debug = ix->debug; tl.counters = ix->counters;
         tl.opt_smem_lists = ix->opt_smem_lists; tl.opt_cta_group = ix->opt_cta_group;
         int64_t fallback = 0, launches = 0;
         std::string err;
@@ -291,6 +292,8 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         ix->stats.kernel_launches += launches;
         if (rc != OSML_KNN_OK) return err.empty() ? rc : fail(rc, err);
         ix->stats.fallback_queries += fallback;
+        ix->stats.retry_queries += ix->tensor.retry_queries;
+        ix->tensor.retry_queries = 0;
         ix->stats.tensor_queries += q;
         ix->stats.last_filter_ms = ix->tensor.filter_ms;
         ix->stats.last_filter_launches = ix->tensor.filter_launches;
@@ -330,7 +333,7 @@ int check_predict_args(const osml_knn_index* ix, int64_t q) {
 
 extern "C" {
 
-int osml_knn_abi_version(void) { return 1000; }
+int osml_knn_abi_version(void) { return 1001; }
 
 const char* osml_knn_last_error(void) { return g_last_error.c_str(); }
 
@@ -508,6 +511,7 @@ int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
     if (key == "epi_warps") { ix->opt_epi_warps = (int)value; return OSML_KNN_OK; }
     if (key == "segments") { ix->opt_nseg = (int)value; return OSML_KNN_OK; }
     if (key == "debug") { ix->debug = (int)value; return OSML_KNN_OK; }
+    if (key == "counters") { ix->counters = (int)value; return OSML_KNN_OK; }
     if (key == "smem_lists") { ix->opt_smem_lists = (int)value; return OSML_KNN_OK; }
     if (key == "cta_group") { ix->opt_cta_group = (int)value; return OSML_KNN_OK; }
     if (key == "query_block") { ix->query_block = (int64_t)value; return OSML_KNN_OK; }

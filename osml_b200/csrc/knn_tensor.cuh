@@ -4,13 +4,16 @@
 // k+1 smallest (predict.py:750).  Doing that arithmetic literally costs 3 un-fusable CUDA-core instructions per
 // element (K2).  Here the tensor cores only *filter*:
 //
-//   K0  knn_prep_rows      one streaming pass: centre by the train column means, round to bf16, append three bf16
-//                          columns holding -0.5*|t^|^2 (hi/mid/lo split, exact to 2^-24) to each train row and
-//                          (1, 1, 1) to each query row, record |q^|^2 and the rounding residuals |q^ - (q - c)|.
-//   K1  knn_tc_filter      persistent tcgen05 kernel: acc[q][t] = q^ . t^ - 0.5*|t^|^2 (so |q^ - t^|^2 = |q^|^2 - 2*acc)
+//   K0  knn_prep_rows      one streaming pass: centre by the train column means, round to bf16, record h = 0.5*|t^|^2
+//                          per train row (plus its minimum over every group of 8 rows), |q^|^2 per query and the
+//                          rounding residuals |q^ - (q - c)|.
+//   K1  knn_tc_filter      persistent tcgen05 kernel: score[q][t] = q^ . t^ - h[t] (so |q^ - t^|^2 = |q^|^2 - 2*score)
 //                          with TMA-staged, 128B-swizzled operand tiles and FP32 accumulators in TMEM; the epilogue
 //                          reads each 128 x 256 accumulator tile straight out of TMEM and keeps, per query, the K'
-//                          largest acc per train segment.  The distance matrix never leaves the SM.
+//                          largest scores per train segment.  The distance matrix never leaves the SM.  The tensor
+//                          core only computes the D-long dot products (K = D, no padding columns for the norms): the
+//                          hot path tests a group of 8 columns against thr + min(h over the group), and only the rare
+//                          groups that pass subtract h element by element.
 //   K3  knn_rescore        per query: exact distances of the candidates in the oracle's arithmetic and summation
 //                          order, top-(k+1) by (distance, index), and a completeness proof -- every row the filter
 //                          dropped has acc <= the segment's K'-th best, which bounds its true distance from below
@@ -22,14 +25,21 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <functional>
 #include <string>
 #include <vector>
 
 #include "knn_common.cuh"
 #include "knn_ptx.cuh"
+
+// -DOSML_TC_COUNTERS=1 builds the instrumented variant of the CTA-pair kernel (tools/ablate.sh); the product has none
+#ifndef OSML_TC_COUNTERS
+#define OSML_TC_COUNTERS 0
+#endif
 
 namespace osml {
 
@@ -44,14 +54,15 @@ constexpr int kTcBStageBytes = kTcBN * 128;   // 32 KB
 constexpr int kTcThreads = 384;       // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 constexpr int kTcMaxKPrime = 64;
 constexpr int kTcMaxCand = 512;       // candidates per query K3 handles (slots * K')
-constexpr float kTcPadScore = -3.0e38f;
 
 struct TcParams {
     int nkb;             // K blocks of the padded feature dimension
-    int ksteps;          // UMMA K steps (16 bf16 each) actually needed: ceil((d + 3) / 16)
+    int ksteps;          // UMMA K steps (16 bf16 each) actually needed: ceil(d / 16)
     int nqt;             // query tiles
     int nseg;            // train segments
-    int tiles_per_seg;   // 256-row tiles per segment
+    int nq_single;       // pair kernel: query-tile pairs swept in one item (see tc_pair_item); the others use nseg
+    int tiles_per_seg;   // 256-row tiles per segment (segment s owns tiles s, s + nseg, ...: every segment sees the
+                         // whole range of row norms, in ascending order)
     int tiles_total;
     int kprime;          // candidates kept per (query, slot)
     int epi_warps;       // 4 or 8
@@ -61,7 +72,12 @@ struct TcParams {
     int nslot;           // nseg * halves
     float* cand_val;     // [qpad][nslot][kprime]
     int* cand_idx;
-    float* cand_thr;     // [qpad][nslot]: every row the slot dropped has acc <= this (-inf: nothing dropped)
+    float* cand_thr;     // [qpad][nslot]: every row the slot dropped has score <= this (-inf: nothing dropped)
+    const float* h;      // [npad] 0.5*|t^|^2 (+inf for padding rows)
+    const float* hmin8;  // [npad / 8] minimum of h over each group of 8 rows
+    const float* hblk;   // [tiles][288]: the same per 256-row tile, h then the 32 group minima (pair kernel, bulk copies)
+    unsigned long long* dbg;   // counters != 0: cycle counters (see tc_neighbours_block)
+    int counters;
     int debug;           // ablation switch for profiling: 1 = epilogue skips TMEM loads, 2 = loads but no selection
 };
 
@@ -105,28 +121,18 @@ struct TcPrepStats {          // device-side reductions over the train rows
     int nonfinite;
 };
 
-// one warp per row
-template <bool kTrain>
-__global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t npad, int d, int dp,
-                                    const float* __restrict__ center, __nv_bfloat16* __restrict__ out,
-                                    double* __restrict__ norm2, double* __restrict__ err, TcPrepStats* stats) {
+// Pass A over the train rows (one warp per row): h = 0.5*|t^|^2 of the centred, bf16-rounded row, the rounding residual
+// |t^ - (t - c)| and the maxima the completeness bound needs.  h is the sort key of the filter copy.
+__global__ void tc_train_norms_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ center,
+                                      float* __restrict__ half_norm, int* __restrict__ iota, TcPrepStats* stats) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= npad) return;
-    __nv_bfloat16* o = out + row * dp;
-    if (row >= n) {                       // padding row: can never be selected (train) / is ignored (queries)
-        for (int j = lane; j < dp; j += 32) o[j] = __float2bfloat16(0.0f);
-        if (kTrain && lane == 0) o[d] = __float2bfloat16(kTcPadScore);
-        if (!kTrain && lane == 0 && norm2) { norm2[row] = 0.0; err[row] = 0.0; }
-        return;
-    }
+    if (row >= n) return;
     const float* xr = x + row * d;
     double n2 = 0.0, e2 = 0.0;
     for (int j = lane; j < d; j += 32) {
         const float v = xr[j], c = center[j];
-        const __nv_bfloat16 h = __float2bfloat16_rn(__fsub_rn(v, c));
-        o[j] = h;
-        const double hd = (double)__bfloat162float(h);
+        const double hd = (double)__bfloat162float(__float2bfloat16_rn(__fsub_rn(v, c)));
         const double diff = hd - ((double)v - (double)c);
         n2 += hd * hd;
         e2 += diff * diff;
@@ -135,28 +141,84 @@ __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int6
         n2 += __shfl_xor_sync(0xffffffffu, n2, off);
         e2 += __shfl_xor_sync(0xffffffffu, e2, off);
     }
-    for (int j = d + 3 + lane; j < dp; j += 32) o[j] = __float2bfloat16(0.0f);
     if (lane == 0) {
-        const double e = sqrt(e2) * (1.0 + 1e-12);
-        if (kTrain) {
-            const double h = -0.5 * n2;
-            const __nv_bfloat16 h1 = __double2bfloat16(h);
-            const double r1 = h - (double)__bfloat162float(h1);
-            const __nv_bfloat16 h2 = __double2bfloat16(r1);
-            const double r2 = r1 - (double)__bfloat162float(h2);
-            const __nv_bfloat16 h3 = __double2bfloat16(r2);
-            o[d] = h1; o[d + 1] = h2; o[d + 2] = h3;
-            const double tn = sqrt(n2) * (1.0 + 1e-12);
-            if (!(n2 < 1.0e37) || !(e2 < 1.0e37)) atomicExch(&stats->nonfinite, 1);
-            else {
-                atomicMax(&stats->et_max_bits, (unsigned long long)__double_as_longlong(e));
-                atomicMax(&stats->tnorm_max_bits, (unsigned long long)__double_as_longlong(tn));
-            }
-        } else {
-            o[d] = __float2bfloat16(1.0f); o[d + 1] = __float2bfloat16(1.0f); o[d + 2] = __float2bfloat16(1.0f);
-            norm2[row] = n2;
-            err[row] = e;     // NaN / inf propagate and make the query fall back
+        half_norm[row] = (float)(0.5 * n2);          // round to nearest: 2^-24 relative, part of TcBounds::c_mma
+        iota[row] = (int)row;
+        if (!(n2 < 1.0e37) || !(e2 < 1.0e37)) atomicExch(&stats->nonfinite, 1);
+        else {
+            atomicMax(&stats->et_max_bits, (unsigned long long)__double_as_longlong(sqrt(e2) * (1.0 + 1e-12)));
+            atomicMax(&stats->tnorm_max_bits, (unsigned long long)__double_as_longlong(sqrt(n2) * (1.0 + 1e-12)));
         }
+    }
+}
+
+// Pass B (one warp per row of the filter copy): position i holds train row perm[i] (rows sorted by ascending h, so the
+// rows nearest to the centre -- the likeliest neighbours of any query -- are scanned first and the per-query
+// thresholds settle early; groups of 8 consecutive rows also get nearly equal h, which keeps the group test tight).
+// Queries (kTrain == false) keep their order and also record |q^|^2 and |q^ - (q - c)|.
+template <bool kTrain>
+__global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t npad, int d, int dp,
+                                    const float* __restrict__ center, const int* __restrict__ perm,
+                                    __nv_bfloat16* __restrict__ out, double* __restrict__ norm2,
+                                    double* __restrict__ err, float* __restrict__ half_norm_sorted,
+                                    int* __restrict__ perm_pad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= npad) return;
+    __nv_bfloat16* o = out + row * dp;
+    if (row >= n) {                       // padding row: can never be selected (train) / is ignored (queries)
+        for (int j = lane; j < dp; j += 32) o[j] = __float2bfloat16(0.0f);
+        if (kTrain && lane == 0) { half_norm_sorted[row] = INFINITY; perm_pad[row] = -1; }
+        if (!kTrain && lane == 0 && norm2) { norm2[row] = 0.0; err[row] = 0.0; }
+        return;
+    }
+    const float* xr = x + (kTrain ? (int64_t)perm[row] : row) * d;
+    double n2 = 0.0, e2 = 0.0;
+    for (int j = lane; j < d; j += 32) {
+        const float v = xr[j], c = center[j];
+        const __nv_bfloat16 h = __float2bfloat16_rn(__fsub_rn(v, c));
+        o[j] = h;
+        if (!kTrain) {
+            const double hd = (double)__bfloat162float(h);
+            const double diff = hd - ((double)v - (double)c);
+            n2 += hd * hd;
+            e2 += diff * diff;
+        }
+    }
+    for (int j = d + lane; j < dp; j += 32) o[j] = __float2bfloat16(0.0f);
+    if (!kTrain) {
+        for (int off = 16; off > 0; off >>= 1) {
+            n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+            e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+        }
+        if (lane == 0) {
+            norm2[row] = n2;
+            err[row] = sqrt(e2) * (1.0 + 1e-12);     // NaN / inf propagate and make the query fall back
+        }
+    }
+}
+
+// per 256-row tile: [256 x h][32 x min(h) over groups of 8 rows][min(h) of each half and of the tile] -- one 1168-byte
+// bulk copy per tile in the pair kernel
+constexpr int kTcHBlock = kTcBN + kTcBN / 8 + 4;     // floats per tile: h, group minima, min of columns 0-127 / 128-255 / all, pad
+__global__ void tc_hblock_kernel(const float* __restrict__ h, int64_t npad, float* __restrict__ hmin8,
+                                 float* __restrict__ hblk) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // group of 8 rows
+    if (g >= npad / 8) return;
+    const float4 a = reinterpret_cast<const float4*>(h)[2 * g], b = reinterpret_cast<const float4*>(h)[2 * g + 1];
+    const float m = fminf(fminf(fminf(a.x, a.y), fminf(a.z, a.w)), fminf(fminf(b.x, b.y), fminf(b.z, b.w)));
+    hmin8[g] = m;
+    const int64_t tile = g / (kTcBN / 8), gi = g % (kTcBN / 8);
+    float* blk = hblk + tile * kTcHBlock;
+    reinterpret_cast<float4*>(blk)[2 * gi] = a;
+    reinterpret_cast<float4*>(blk)[2 * gi + 1] = b;
+    blk[kTcBN + gi] = m;
+    if (gi == 0) {                                   // one thread per tile: minima over 128 / 128 / 256 rows
+        float m0 = INFINITY, m1 = INFINITY;
+        for (int j = 0; j < kTcBN / 2; ++j) m0 = fminf(m0, h[tile * kTcBN + j]);
+        for (int j = kTcBN / 2; j < kTcBN; ++j) m1 = fminf(m1, h[tile * kTcBN + j]);
+        blk[kTcBN + kTcBN / 8] = m0; blk[kTcBN + kTcBN / 8 + 1] = m1;
+        blk[kTcBN + kTcBN / 8 + 2] = fminf(m0, m1); blk[kTcBN + kTcBN / 8 + 3] = 0.0f;
     }
 }
 
@@ -219,59 +281,173 @@ __device__ __forceinline__ float tc_list_min(const float (&lv)[KP]) {
     return m;
 }
 
-// Register-resident candidate list (KP = 16 or 32 entries per thread).
-// Values are "packed": the low log2(KP) mantissa bits of a list entry hold its slot number, and the low 5 bits of an
-// accumulator read from TMEM are replaced by its column inside the 32-column chunk, so a max / min tree returns the
-// value and where it lives in one go.  The perturbation (<= 2^-18 relative) is part of the error budget K3 proves
-// completeness with (TcBounds::c_mma).  All 32 lanes of a warp run the insert rounds together, so a chunk costs
-// max-over-lanes (not sum-over-lanes) of the number of hits.
+// Register-resident candidate list (KP = 16 or 32 entries per thread) fed through a small per-thread shared-memory
+// buffer.
+// List values are "packed": the low log2(KP) mantissa bits of an entry hold its slot number, so a min tree returns the
+// threshold and where it lives in one go.  The perturbation (<= 2^-19 relative) is part of the error budget K3 proves
+// completeness with (TcBounds::c_mma).
+// The hot path only asks "does any lane of the warp see a value above its threshold in this group of 8 columns?" and
+// collects the answers in a warp-uniform bit mask.  The rare groups that hit go through ONE out-of-line-sized code
+// region (so the instruction cache holds a single copy): the group's 8 values are appended to the thread's buffer (a
+// predicated 8-byte store each), and the warp then flushes the buffers into the lists in rounds -- round r inserts
+// entry r of every lane that has one.  Everything dropped anywhere is <= the list minimum at that time <= the final
+// threshold.
+constexpr int kTcHSlots = 8;          // ring of per-tile h blocks in the pair kernel
+constexpr int kTcBufCap = 16;         // buffered candidates per thread; a flush is forced above kTcBufCap - 8
+
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void lds_v2(uint32_t addr, uint32_t& a, uint32_t& b) {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
+}
+
 template <int KP>
 struct TcRegList {
     static constexpr uint32_t kSlotMask = KP - 1;
     float lv[KP];
     int lr[KP];
     float thr;
+    uint32_t buf_addr;     // shared-memory address of this thread's buffer entry 0
+    uint32_t buf_stride;   // bytes between consecutive entries of one thread (= epilogue threads * 8)
+    int cnt;               // buffered candidates
+    int rd;                // ... of which already fed to the list
+    int buf_shift;         // log2(buf_stride): the epilogue has 128 or 256 threads
+    __device__ __forceinline__ void attach(uint32_t addr, uint32_t stride) {
+        buf_addr = addr; buf_stride = stride; buf_shift = 31 - __clz((int)stride); cnt = 0; rd = 0;
+    }
     // empty slots hold -FLT_MAX, or a seed threshold proven elsewhere (values at or below it are never inserted)
     __device__ __forceinline__ void reset(float seed = -INFINITY) {
         const uint32_t base = seed > -3.0e38f ? __float_as_uint(seed) : 0xFF7FFFFFu;
 #pragma unroll
         for (int e = 0; e < KP; ++e) { lv[e] = __uint_as_float((base & ~kSlotMask) | (uint32_t)e); lr[e] = -1; }
         thr = tc_list_min<KP>(lv);
+        cnt = 0;
+        rd = 0;
     }
-    __device__ __forceinline__ void insert(float cur, int row) {
-        const uint32_t slot = __float_as_uint(thr) & kSlotMask;
-        const float nv = __uint_as_float((__float_as_uint(cur) & ~kSlotMask) | slot);
+    // branch-free insert (a select per entry): lanes with take == false match no slot
+    __device__ __forceinline__ void insert_sel(bool take, float cur, int row) {
+        const uint32_t slot = take ? (__float_as_uint(thr) & kSlotMask) : 0xFFFFFFFFu;
+        const uint32_t nvb = (__float_as_uint(cur) & ~kSlotMask) | (slot & kSlotMask);
 #pragma unroll
-        for (int e = 0; e < KP; ++e)
-            if (slot == (uint32_t)e) { lv[e] = nv; lr[e] = row; }
+        for (int e = 0; e < KP; ++e) {
+            uint32_t vb = __float_as_uint(lv[e]);
+            asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, %3;\n\tselp.b32 %0, %4, %0, p;\n\tselp.b32 %1, %5, %1, p;\n\t}"
+                : "+r"(vb), "+r"(lr[e]) : "r"(slot), "r"((uint32_t)e), "r"(nvb), "r"(row));
+            lv[e] = __uint_as_float(vb);
+        }
         thr = tc_list_min<KP>(lv);
     }
-    // one group of 8 columns: only entered (warp-uniformly) when some lane has a value above its threshold there
-    template <int G>
-    __device__ __forceinline__ void scan_group(const float (&v)[32], int row0) {
-        float w[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = __uint_as_float((__float_as_uint(v[8 * G + j]) & ~7u) | (uint32_t)j);
-        float cur = tc_max8(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
-        while (__any_sync(0xffffffffu, cur > thr)) {
-            if (cur > thr) insert(cur, row0 + 8 * G + (int)(__float_as_uint(cur) & 7u));
-            cur = tc_max8(tc_sel_below(w[0], cur), tc_sel_below(w[1], cur), tc_sel_below(w[2], cur),
-                          tc_sel_below(w[3], cur), tc_sel_below(w[4], cur), tc_sel_below(w[5], cur),
-                          tc_sel_below(w[6], cur), tc_sel_below(w[7], cur));
-        }
+    // warp-collective: every lane with unread buffer entries feeds its oldest one to its list.  Callers run rounds
+    // while they wait for the next accumulator tile, so list maintenance rides on otherwise idle issue slots.
+    __device__ __forceinline__ void flush_round() {
+        uint32_t vb = 0xFF800000u, rb = 0;          // -inf: lanes without an unread entry never insert
+        const bool have = rd < cnt;
+        if (have) lds_v2(buf_addr + (uint32_t)rd * buf_stride, vb, rb);
+        rd += have ? 1 : 0;
+        const float val = __uint_as_float(vb);
+        const bool take = val > thr;
+        if (__any_sync(0xffffffffu, take)) insert_sel(take, val, (int)rb);
+        if (!__any_sync(0xffffffffu, rd < cnt)) { cnt = 0; rd = 0; }    // linear buffers: rewind once all are drained
     }
-    __device__ __forceinline__ void scan(const float (&v)[32], int row0) {
+    __device__ __forceinline__ bool pending() const { return __any_sync(0xffffffffu, rd < cnt); }
+    __device__ __forceinline__ void flush() {
+#pragma unroll 1
+        while (pending()) flush_round();
+    }
+    // appends the values above the threshold (branch-free: a predicated 8-byte store and a predicated bump each)
+    // columns OFF .. OFF+7 of chunk v (train rows row0 .. row0+7, their h in ha | hb)
+    template <int OFF>
+    __device__ __forceinline__ void append_group(const float (&v)[32], const float4 ha, const float4 hb, int row0) {
+        const float hh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+        uint32_t waddr = buf_addr + (uint32_t)cnt * buf_stride;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float w = v[OFF + j] - hh[j];
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p st.shared.v2.b32 [%0], {%1, %3};\n\t"
+                "@p add.u32 %0, %0, %4;\n\t}"
+                : "+r"(waddr)
+                : "f"(w), "f"(thr), "r"(row0 + j), "r"(buf_stride)
+                : "memory");
+        }
+        cnt = (int)((waddr - buf_addr) >> buf_shift);
+    }
+    // warp-uniform 4-bit mask: bit g set when some lane may have a score above its threshold in columns 8g .. 8g+7 of
+    // the chunk.  v holds the raw dot products; score = v - h[column], and hm holds min(h) of the chunk's 4 groups, so
+    // max(v over the group) <= thr + min(h) rules the whole group out without touching h.
+    __device__ __forceinline__ uint32_t hits(const float (&v)[32], const float4 hm) const {
         const float g0 = tc_max8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
         const float g1 = tc_max8(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
         const float g2 = tc_max8(v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23]);
         const float g3 = tc_max8(v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]);
-        const float mx = fmaxf(fmaxf(g0, g1), fmaxf(g2, g3));
-        if (__any_sync(0xffffffffu, mx > thr)) {
-            if (__any_sync(0xffffffffu, g0 > thr)) scan_group<0>(v, row0);
-            if (__any_sync(0xffffffffu, g1 > thr)) scan_group<1>(v, row0);
-            if (__any_sync(0xffffffffu, g2 > thr)) scan_group<2>(v, row0);
-            if (__any_sync(0xffffffffu, g3 > thr)) scan_group<3>(v, row0);
+        const bool p0 = g0 > thr + hm.x, p1 = g1 > thr + hm.y, p2 = g2 > thr + hm.z, p3 = g3 > thr + hm.w;
+        uint32_t m = 0;
+        if (__any_sync(0xffffffffu, p0 | p1 | p2 | p3)) {
+            m = (__any_sync(0xffffffffu, p0) ? 1u : 0u) | (__any_sync(0xffffffffu, p1) ? 2u : 0u) |
+                (__any_sync(0xffffffffu, p2) ? 4u : 0u) | (__any_sync(0xffffffffu, p3) ? 8u : 0u);
         }
+        return m;
+    }
+    // per-lane version of the same test (no votes): bit g set when THIS lane may have a hit in group g of the chunk.
+    // OR-ing the four chunks' bits (shifted) and one __reduce_or_sync gives the warp-uniform mask of a whole tile.
+    __device__ __forceinline__ uint32_t lane_bits(const float (&v)[32], const float4 hm) const {
+        const float g0 = tc_max8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        const float g1 = tc_max8(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+        const float g2 = tc_max8(v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23]);
+        const float g3 = tc_max8(v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]);
+        return (g0 > thr + hm.x ? 1u : 0u) | (g1 > thr + hm.y ? 2u : 0u) | (g2 > thr + hm.z ? 4u : 0u) |
+               (g3 > thr + hm.w ? 8u : 0u);
+    }
+    // slow path over the chunks held in registers; `mask` has one bit per group of 8 columns of v0 | v1 | v2 | v3;
+    // h of column 0 of v0 is at hrow (global memory) or, with kSmemH, at shared-memory address h_saddr
+    template <bool kSmemH>
+    __device__ __forceinline__ void drain(uint32_t mask, const float (&v0)[32], const float (&v1)[32],
+                                          const float (&v2)[32], const float (&v3)[32], int row0,
+                                          const float* __restrict__ hrow, uint32_t h_saddr) {
+#pragma unroll 1
+        while (mask != 0) {
+            const int g = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            float4 ha, hb;
+            if (kSmemH) {
+                ha = lds_f4(h_saddr + 32u * (uint32_t)g);
+                hb = lds_f4(h_saddr + 32u * (uint32_t)g + 16u);
+            } else {
+                ha = __ldg(reinterpret_cast<const float4*>(hrow + 8 * g));
+                hb = __ldg(reinterpret_cast<const float4*>(hrow + 8 * g + 4));
+            }
+            // one statically indexed copy of the 8-element append per group (registers cannot be indexed dynamically,
+            // and gathering the group into a common array first costs more than the append itself)
+            switch (g) {
+#define OSML_TC_CASE(G, ARR, OFF) case G: append_group<OFF>(ARR, ha, hb, row0 + 8 * G); break;
+                OSML_TC_CASE(0, v0, 0) OSML_TC_CASE(1, v0, 8) OSML_TC_CASE(2, v0, 16) OSML_TC_CASE(3, v0, 24)
+                OSML_TC_CASE(4, v1, 0) OSML_TC_CASE(5, v1, 8) OSML_TC_CASE(6, v1, 16) OSML_TC_CASE(7, v1, 24)
+                OSML_TC_CASE(8, v2, 0) OSML_TC_CASE(9, v2, 8) OSML_TC_CASE(10, v2, 16) OSML_TC_CASE(11, v2, 24)
+                OSML_TC_CASE(12, v3, 0) OSML_TC_CASE(13, v3, 8) OSML_TC_CASE(14, v3, 16)
+                default: append_group<24>(v3, ha, hb, row0 + 120); break;
+#undef OSML_TC_CASE
+            }
+            // forced catch-up when a buffer nears its capacity (mostly in the first tiles of a sweep, when every
+            // value beats the threshold); otherwise the lists catch up while the warp waits for its next tile
+            if (__any_sync(0xffffffffu, cnt > kTcBufCap - 8)) flush();
+        }
+    }
+    // one 32-column chunk starting at train row row0 (hm: the 4 group minima of h)
+    template <bool kSmemH>
+    __device__ __forceinline__ void scan(const float (&v)[32], int row0, const float4 hm, const float* __restrict__ hrow,
+                                         uint32_t h_saddr) {
+        const uint32_t m = hits(v, hm);
+        if (m) drain<kSmemH>(m, v, v, v, v, row0, hrow, h_saddr);
+    }
+    __device__ __forceinline__ void scan(const float (&v)[32], int row0, const float* __restrict__ h,
+                                         const float* __restrict__ hmin8) {
+        scan<false>(v, row0, __ldg(reinterpret_cast<const float4*>(hmin8 + (row0 >> 3))), h + row0, 0u);
     }
 };
 
@@ -286,8 +462,9 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const uint32_t ring_stage_bytes = p.a_resident ? kTcBStageBytes : kTcABlockBytes + kTcBStageBytes;
     const uint32_t ring_b_offset = p.a_resident ? 0 : kTcABlockBytes;      // streamed mode: [A block][B block]
     const int epi_threads = p.epi_warps * 32;
-    const size_t list_elems = KP > 0 ? 0 : (size_t)p.kprime * epi_threads;   // register lists need no shared memory
-    float* list_val = reinterpret_cast<float*>(b_smem + (size_t)p.stages * ring_stage_bytes);
+    const size_t list_elems = KP > 0 ? 0 : (size_t)p.kprime * epi_threads;   // register lists only need the buffer
+    unsigned char* cand_buf = b_smem + (size_t)p.stages * ring_stage_bytes;  // [kTcBufCap][epi_threads] x 8 B
+    float* list_val = reinterpret_cast<float*>(cand_buf + (KP > 0 ? (size_t)kTcBufCap * epi_threads * 8 : 0));
     int* list_idx = reinterpret_cast<int*>(list_val + list_elems);
     uint64_t* bars = reinterpret_cast<uint64_t*>(list_idx + list_elems);
     uint64_t* full_bar = bars;                    // [stages]
@@ -324,8 +501,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             uint32_t stage = 0, phase = 0, it = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
                 const int seg = item / p.nqt, qt = item % p.nqt;
-                const int tile0 = seg * p.tiles_per_seg;
-                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+                const int tile0 = seg;                                   // segments interleave: tiles seg, seg + nseg, ...
+                const int ntiles = (p.tiles_total - seg + p.nseg - 1) / p.nseg;
                 if (p.a_resident) {
                     ptx::mbar_wait(a_empty, (it & 1) ^ 1);
                     ptx::mbar_expect_tx(a_full, (uint32_t)p.nkb * kTcABlockBytes);
@@ -333,7 +510,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         ptx::tma_load_2d(a_smem + (size_t)kb * kTcABlockBytes, &map_a, a_full, kb * kTcKB, qt * kTcBM);
                 }
                 for (int t = 0; t < ntiles; ++t) {
-                    const int row0 = (tile0 + t) * kTcBN;
+                    const int row0 = (tile0 + t * p.nseg) * kTcBN;
                     for (int kb = 0; kb < p.nkb; ++kb) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                         unsigned char* ring = b_smem + (size_t)stage * ring_stage_bytes;
@@ -358,8 +535,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             uint32_t stage = 0, phase = 0, it = 0, acc_it = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
                 const int seg = item / p.nqt;
-                const int tile0 = seg * p.tiles_per_seg;
-                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+                const int tile0 = seg;                                   // segments interleave: tiles seg, seg + nseg, ...
+                const int ntiles = (p.tiles_total - seg + p.nseg - 1) / p.nseg;
                 if (p.a_resident) {
                     ptx::mbar_wait(a_full, it & 1);
                     ptx::tc_fence_after();
@@ -401,10 +578,11 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         uint32_t acc_it = 0;
         if constexpr (KP > 0) {
             TcRegList<KP> list;
+            list.attach(ptx::smem_u32(cand_buf) + (uint32_t)et * 8u, (uint32_t)epi_threads * 8u);
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int seg = item / p.nqt, qt = item % p.nqt;
-                const int tile0 = seg * p.tiles_per_seg;
-                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+                const int tile0 = seg;                                   // segments interleave: tiles seg, seg + nseg, ...
+                const int ntiles = (p.tiles_total - seg + p.nseg - 1) / p.nseg;
                 list.reset();
                 if (p.debug == 4) list.thr = INFINITY;   // ablation: fast path only
                 for (int t = 0; t < ntiles; ++t, ++acc_it) {
@@ -412,7 +590,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     ptx::mbar_wait(&tmem_full[as], aphase);
                     ptx::tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
-                    const int row_base = (tile0 + t) * kTcBN + half * cols;
+                    const int row_base = (tile0 + t * p.nseg) * kTcBN + half * cols;
                     if (p.debug != 1 && p.debug != 3) {
                         if constexpr (KP <= 16) {
                             float va[32], vb[32];
@@ -420,11 +598,11 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                             for (int c = 0; c < cols; c += 64) {   // two chunks per trip, loads one chunk ahead
                                 ptx::tmem_ld_wait();
                                 ptx::tmem_ld_32x32(taddr + c + 32, vb);
-                                if (p.debug != 2) list.scan(va, row_base + c);
+                                if (p.debug != 2) list.scan(va, row_base + c, p.h, p.hmin8);
                                 else if (va[0] + va[31] == 12345.678f) list.thr = va[0];
                                 ptx::tmem_ld_wait();
                                 if (c + 64 < cols) ptx::tmem_ld_32x32(taddr + c + 64, va);
-                                if (p.debug != 2) list.scan(vb, row_base + c + 32);
+                                if (p.debug != 2) list.scan(vb, row_base + c + 32, p.h, p.hmin8);
                                 else if (vb[0] + vb[31] == 12345.678f) list.thr = vb[0];
                             }
                         } else {
@@ -432,7 +610,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                                 float va[32];
                                 ptx::tmem_ld_32x32(taddr + c, va);
                                 ptx::tmem_ld_wait();
-                                list.scan(va, row_base + c);
+                                list.scan(va, row_base + c, p.h, p.hmin8);
                             }
                         }
                     }
@@ -440,6 +618,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
                 }
+                list.flush();
                 const size_t q = (size_t)qt * kTcBM + m;
                 const size_t slot = (size_t)seg * halves + half;
                 float* ov = p.cand_val + (q * p.nslot + slot) * KP;
@@ -454,8 +633,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const uint32_t val_addr = ptx::smem_u32(list_val + et), idx_addr = ptx::smem_u32(list_idx + et);
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int seg = item / p.nqt, qt = item % p.nqt;
-                const int tile0 = seg * p.tiles_per_seg;
-                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
+                const int tile0 = seg;                                   // segments interleave: tiles seg, seg + nseg, ...
+                const int ntiles = (p.tiles_total - seg + p.nseg - 1) / p.nseg;
                 for (int e = 0; e < p.kprime; ++e) {
                     sts_b32(val_addr + e * stride_bytes, __float_as_uint(-INFINITY));
                     sts_b32(idx_addr + e * stride_bytes, 0xffffffffu);
@@ -463,13 +642,15 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 float thr = -INFINITY;
                 uint32_t pos_min = 0;
                 auto scan = [&](const float (&v)[32], int row0) {
+                    const float4 hm = __ldg(reinterpret_cast<const float4*>(p.hmin8 + (row0 >> 3)));
                     const float mx = tc_max32(v);
-                    if (mx > thr) {
+                    if (mx > thr + fminf(fminf(hm.x, hm.y), fminf(hm.z, hm.w))) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            if (v[i] > thr) {
+                            const float sc = v[i] - __ldg(p.h + row0 + i);
+                            if (sc > thr) {
                                 const unsigned long long r =
-                                    tc_list_insert(val_addr, idx_addr, p.kprime, stride_bytes, pos_min, v[i], row0 + i);
+                                    tc_list_insert(val_addr, idx_addr, p.kprime, stride_bytes, pos_min, sc, row0 + i);
                                 thr = __uint_as_float((uint32_t)r);
                                 pos_min = (uint32_t)(r >> 32);
                             }
@@ -481,7 +662,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     ptx::mbar_wait(&tmem_full[as], aphase);
                     ptx::tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
-                    const int row_base = (tile0 + t) * kTcBN + half * cols;
+                    const int row_base = (tile0 + t * p.nseg) * kTcBN + half * cols;
                     float va[32], vb[32];
                     if (p.debug != 1 && p.debug != 3) {
                         ptx::tmem_ld_32x32(taddr, va);
@@ -534,6 +715,17 @@ constexpr int kTcBHalfBytes = (kTcBN / 2) * 128;      // 16 KB: this CTA's half 
 // a ring stage of the pair kernel holds ALL K blocks of this CTA's half tile (nkb * 16 KB): one barrier round trip and
 // one wait per tile keep the single MMA-issuing thread off the critical path
 
+// Work items of the pair kernel.  Query-tile pairs 0 .. nq_single-1 are swept over the whole train set in ONE item
+// (one warm-up of the candidate lists, the tightest thresholds); the remaining pairs -- those that would leave most of
+// the machine idle in a last partial wave -- are split into nseg interleaved segments (tiles seg, seg + nseg, ...).
+struct TcItem { int qp, seg, nsg; };
+__device__ __forceinline__ TcItem tc_pair_item(const TcParams& p, int item) {
+    TcItem r;
+    if (item < p.nq_single) { r.qp = item; r.seg = 0; r.nsg = 1; }
+    else { const int j = item - p.nq_single; r.qp = p.nq_single + j / p.nseg; r.seg = j % p.nseg; r.nsg = p.nseg; }
+    return r;
+}
+
 template <int KP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -542,21 +734,25 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     unsigned char* a_smem = smem;
     unsigned char* b_smem = a_smem + (size_t)p.nkb * kTcABlockBytes;
     const uint32_t stage_bytes = (uint32_t)p.nkb * kTcBHalfBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)p.stages * stage_bytes);
+    const int epi_threads = p.epi_warps * 32;
+    unsigned char* cand_buf = b_smem + (size_t)p.stages * stage_bytes;         // [kTcBufCap][epi_threads] x 8 B
+    unsigned char* h_ring = cand_buf + (size_t)kTcBufCap * epi_threads * 8;     // [kTcHSlots][kTcHBlock] floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(h_ring + (size_t)kTcHSlots * kTcHBlock * 4);
     uint64_t* full_bar = bars;                    // [stages]  (used in the leader)
     uint64_t* empty_bar = bars + 8;               // [stages]
     uint64_t* tmem_full = bars + 16;              // [2]
     uint64_t* tmem_empty = bars + 18;             // [2]       (used in the leader)
     uint64_t* a_full = bars + 20;                 //           (used in the leader)
     uint64_t* a_empty = bars + 21;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    uint64_t* h_full = bars + 24;                 // [kTcHSlots]  this CTA's copy of the tile's h block has landed
+    uint64_t* h_empty = bars + 24 + kTcHSlots;    // [kTcHSlots]  ... and every epilogue warp is done with it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24 + 2 * kTcHSlots);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = rank == 0;
-    const int epi_threads = p.epi_warps * 32;
     const int nqp = p.nqt / 2;                    // query-tile pairs (host pads nqt to even)
-    const int nitems = nqp * p.nseg;
+    const int nitems = p.nq_single + (nqp - p.nq_single) * p.nseg;
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
@@ -568,6 +764,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 2 * p.epi_warps); }
         ptx::mbar_init(a_full, 2);
         ptx::mbar_init(a_empty, 1);
+        for (int s = 0; s < kTcHSlots; ++s) { ptx::mbar_init(&h_full[s], 1); ptx::mbar_init(&h_empty[s], p.epi_warps); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc_pair(tmem_slot, 512);
@@ -575,148 +772,243 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     ptx::cluster_sync_all();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // 384 threads x 168 registers at launch: warps 0-3 keep 56 each, the two epilogue warpgroups get 224 each
+    if (warp < 4) {
+        ptx::setmaxnreg_dec<56>();
 
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer (both CTAs): own query tile, own half of each train tile =====
-            uint32_t stage = 0, phase = 0, it = 0;
-            for (int item = cluster_id; item < nitems; item += nclusters, ++it) {
-                const int seg = item / nqp, qt = 2 * (item % nqp) + (int)rank;
-                const int tile0 = seg * p.tiles_per_seg;
-                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
-                ptx::mbar_wait(a_empty, (it & 1) ^ 1);
-                if (leader) ptx::mbar_expect_tx(a_full, 2u * (uint32_t)p.nkb * kTcABlockBytes);
-                else ptx::mbar_arrive_remote(a_full, 0);
-                for (int kb = 0; kb < p.nkb; ++kb)
-                    ptx::tma_load_2d_pair(a_smem + (size_t)kb * kTcABlockBytes, &map_a, a_full, kb * kTcKB, qt * kTcBM);
-                for (int t = 0; t < ntiles; ++t) {
-                    const int row0 = (tile0 + t) * kTcBN + (int)rank * (kTcBN / 2);
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (p.debug == 3) {                          // ablation: no operand traffic
-                        if (leader) ptx::mbar_arrive(&full_bar[stage]);
-                        else ptx::mbar_arrive_remote(&full_bar[stage], 0);
-                    } else {
-                        if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
-                        else ptx::mbar_arrive_remote(&full_bar[stage], 0);
-                        for (int kb = 0; kb < p.nkb; ++kb)
-                            ptx::tma_load_2d_pair(b_smem + (size_t)stage * stage_bytes + (size_t)kb * kTcBHalfBytes,
-                                                  &map_b, &full_bar[stage], kb * kTcKB, row0);
+        if (warp == 0) {
+            if (lane == 0) {
+                // ===== TMA producer (both CTAs): own query tile, own half of each train tile =====
+                uint32_t stage = 0, phase = 0, it = 0, hslot = 0, hphase = 0;
+                for (int item = cluster_id; item < nitems; item += nclusters, ++it) {
+                    const TcItem wi = tc_pair_item(p, item);
+                    const int seg = wi.seg, nsg = wi.nsg, qt = 2 * wi.qp + (int)rank;
+                    const int tile0 = seg;
+                    const int ntiles = (p.tiles_total - seg + nsg - 1) / nsg;
+                    ptx::mbar_wait(a_empty, (it & 1) ^ 1);
+                    if (leader) ptx::mbar_expect_tx(a_full, 2u * (uint32_t)p.nkb * kTcABlockBytes);
+                    else ptx::mbar_arrive_remote(a_full, 0);
+                    for (int kb = 0; kb < p.nkb; ++kb)
+                        ptx::tma_load_2d_pair(a_smem + (size_t)kb * kTcABlockBytes, &map_a, a_full, kb * kTcKB, qt * kTcBM);
+                    for (int t = 0; t < ntiles; ++t) {
+                        const int row0 = (tile0 + t * nsg) * kTcBN + (int)rank * (kTcBN / 2);
+                        // this CTA's copy of the tile's h block (256 x h, 32 group minima) for its epilogue warps
+                        ptx::mbar_wait(&h_empty[hslot], hphase ^ 1);
+                        ptx::mbar_expect_tx(&h_full[hslot], kTcHBlock * 4);
+                        ptx::bulk_load_1d(h_ring + (size_t)hslot * kTcHBlock * 4, p.hblk + (size_t)(tile0 + t * nsg) * kTcHBlock,
+                                          kTcHBlock * 4, &h_full[hslot]);
+                        if (++hslot == (uint32_t)kTcHSlots) { hslot = 0; hphase ^= 1; }
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (p.debug == 3) {                          // ablation: no operand traffic
+                            if (leader) ptx::mbar_arrive(&full_bar[stage]);
+                            else ptx::mbar_arrive_remote(&full_bar[stage], 0);
+                        } else {
+                            if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+                            else ptx::mbar_arrive_remote(&full_bar[stage], 0);
+                            for (int kb = 0; kb < p.nkb; ++kb)
+                                ptx::tma_load_2d_pair(b_smem + (size_t)stage * stage_bytes + (size_t)kb * kTcBHalfBytes,
+                                                      &map_b, &full_bar[stage], kb * kTcKB, row0);
+                        }
+                        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && leader) {
-            // ===== MMA issuer (leader CTA only) =====
-            const uint32_t idesc = ptx::umma_idesc_bf16(2 * kTcBM, kTcBN);
-            const uint32_t hi = ptx::umma_desc_hi_k_sw128();
-            const uint32_t a_lo0 = ptx::umma_desc_lo(ptx::smem_u32(a_smem)), b_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_smem));
-            uint32_t stage = 0, phase = 0, it = 0, acc_it = 0;
-            for (int item = cluster_id; item < nitems; item += nclusters, ++it) {
-                const int seg = item / nqp;
-                const int tile0 = seg * p.tiles_per_seg;
-                const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
-                ptx::mbar_wait(a_full, it & 1);
-                ptx::tc_fence_after();
-                for (int t = 0; t < ntiles; ++t, ++acc_it) {
-                    const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
-                    ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
-                    ptx::mbar_wait(&full_bar[stage], phase);
+        } else if (warp == 1) {
+            if (lane == 0 && leader) {
+                // ===== MMA issuer (leader CTA only) =====
+                const uint32_t idesc = ptx::umma_idesc_bf16(2 * kTcBM, kTcBN);
+                const uint32_t hi = ptx::umma_desc_hi_k_sw128();
+                const uint32_t a_lo0 = ptx::umma_desc_lo(ptx::smem_u32(a_smem)), b_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_smem));
+                uint32_t stage = 0, phase = 0, it = 0, acc_it = 0;
+                long long dbg_wait_acc = 0, dbg_wait_ops = 0;
+                const long long dbg_t0 = clock64();
+                for (int item = cluster_id; item < nitems; item += nclusters, ++it) {
+                    const TcItem wi = tc_pair_item(p, item);
+                    const int ntiles = (p.tiles_total - wi.seg + wi.nsg - 1) / wi.nsg;
+                    ptx::mbar_wait(a_full, it & 1);
                     ptx::tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + as * kTcBN;
-                    const uint32_t b_lo_stage = b_lo0 + stage * (stage_bytes >> 4);
-                    for (int kb = 0; kb < p.nkb; ++kb) {
-                        const int nks = p.ksteps - kb * 4;
-                        const uint32_t a_lo = a_lo0 + kb * (kTcABlockBytes >> 4);
-                        const uint32_t b_lo = b_lo_stage + kb * (kTcBHalfBytes >> 4);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            if (ks < nks)
-                                ptx::umma_bf16_ss_pair_lohi(tmem_d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc,
-                                                            (uint32_t)((kb | ks) != 0));
+                    for (int t = 0; t < ntiles; ++t, ++acc_it) {
+                        const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                        if ((OSML_TC_COUNTERS && p.counters)) {      // where does the issuer wait: accumulator stage (epilogue) or operands (TMA)?
+                            const long long t0 = clock64();
+                            ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+                            const long long t1 = clock64();
+                            ptx::mbar_wait(&full_bar[stage], phase);
+                            const long long t2 = clock64();
+                            dbg_wait_acc += t1 - t0; dbg_wait_ops += t2 - t1;
+                        } else {
+                            ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+                            ptx::mbar_wait(&full_bar[stage], phase);
+                        }
+                        ptx::tc_fence_after();
+                        const uint32_t tmem_d = tmem_base + as * kTcBN;
+                        const uint32_t b_lo_stage = b_lo0 + stage * (stage_bytes >> 4);
+                        for (int kb = 0; kb < p.nkb; ++kb) {
+                            const int nks = p.ksteps - kb * 4;
+                            const uint32_t a_lo = a_lo0 + kb * (kTcABlockBytes >> 4);
+                            const uint32_t b_lo = b_lo_stage + kb * (kTcBHalfBytes >> 4);
+    #pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                if (ks < nks)
+                                    ptx::umma_bf16_ss_pair_lohi(tmem_d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc,
+                                                                (uint32_t)((kb | ks) != 0));
+                        }
+                        ptx::umma_commit_pair(&empty_bar[stage]);      // both CTAs may refill this stage
+                        ptx::umma_commit_pair(&tmem_full[as]);         // both CTAs' epilogues may read the tile
+                        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                     }
-                    ptx::umma_commit_pair(&empty_bar[stage]);      // both CTAs may refill this stage
-                    ptx::umma_commit_pair(&tmem_full[as]);         // both CTAs' epilogues may read the tile
-                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                    ptx::umma_commit_pair(a_empty);
                 }
-                ptx::umma_commit_pair(a_empty);
+                if ((OSML_TC_COUNTERS && p.counters)) {
+                    atomicAdd(p.dbg + 0, (unsigned long long)dbg_wait_acc);
+                    atomicAdd(p.dbg + 1, (unsigned long long)dbg_wait_ops);
+                    atomicAdd(p.dbg + 2, (unsigned long long)(clock64() - dbg_t0));
+                }
             }
         }
-    } else if (warp >= 4 && warp < 4 + p.epi_warps) {
-        // ===== epilogue (both CTAs): own 128 query rows x 256 columns of every accumulator tile =====
-        const int ew = warp - 4;
-        const int quarter = ew & 3, half = ew >> 2, halves = p.epi_warps >> 2;
-        const int cols = kTcBN / halves;
-        const int m = quarter * 32 + lane;
-        uint32_t acc_it = 0;
-        TcRegList<KP> list;
-        for (int item = cluster_id; item < nitems; item += nclusters) {
-            const int seg = item / nqp, qt = 2 * (item % nqp) + (int)rank;
-            const int tile0 = seg * p.tiles_per_seg;
-            const int ntiles = min(p.tiles_per_seg, p.tiles_total - tile0);
-            // seed the threshold with what earlier segments of the same query already proved: their K'-th best
-            // bounds this query's answer from below, so rows scoring under it cannot matter here either.  The slots
-            // are written by other CTAs of this launch; an unfinished one still reads -inf (memset before launch).
-            const size_t q = (size_t)qt * kTcBM + m;
-            float seed = -INFINITY;
-            for (int s2 = 0; s2 < seg; ++s2)
-                seed = fmaxf(seed, *(const volatile float*)(p.cand_thr + q * p.nslot + (size_t)s2 * halves + half));
-            list.reset(seed);
-            if (p.debug == 4) list.thr = INFINITY;       // ablation: fast path only
-            for (int t = 0; t < ntiles; ++t, ++acc_it) {
-                const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
-                ptx::mbar_wait(&tmem_full[as], aphase);
-                ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
-                const int row_base = (tile0 + t) * kTcBN + half * cols;
-                bool released = false;
-                if (p.debug != 1 && p.debug != 3) {
-                    if constexpr (KP <= 16) {
-                        // two register buffers; the accumulator stage is handed back to the MMA as soon as the last
-                        // TMEM load has landed, the last two chunks are scanned after the release
-                        float va[32], vb[32];
-                        ptx::tmem_ld_32x32(taddr, va);
-                        ptx::tmem_ld_32x32(taddr + 32, vb);
-                        for (int c = 0; c < cols; c += 64) {
+    } else {
+        ptx::setmaxnreg_inc<224>();
+        if (warp < 4 + p.epi_warps) {
+            // ===== epilogue (both CTAs): own 128 query rows x 256 columns of every accumulator tile =====
+            const int ew = warp - 4;
+            const int quarter = ew & 3, half = ew >> 2, halves = p.epi_warps >> 2;
+            const int cols = kTcBN / halves;
+            const int m = quarter * 32 + lane;
+            uint32_t acc_it = 0, hslot = 0, hphase = 0;
+            TcRegList<KP> list;
+            list.attach(ptx::smem_u32(cand_buf) + (uint32_t)(ew * 32 + lane) * 8u, (uint32_t)epi_threads * 8u);
+            // loop-invariant shared-memory addresses, kept in registers
+            const uint32_t bar_tmem_full = ptx::smem_u32(tmem_full);                          // + 8 * stage
+            const uint32_t bar_tmem_empty = ptx::mapa_u32(ptx::smem_u32(tmem_empty), 0);      // the leader's, + 8 * stage
+            const uint32_t bar_h_full = ptx::smem_u32(h_full), bar_h_empty = ptx::smem_u32(h_empty);   // + 8 * slot
+            const uint32_t h_base = ptx::smem_u32(h_ring) + (uint32_t)(half * cols) * 4u;      // h of this thread's columns
+            const uint32_t hm_base = ptx::smem_u32(h_ring) + kTcBN * 4 + (uint32_t)(half * cols / 8) * 4u;   // their group minima
+            const uint32_t hmin_base = ptx::smem_u32(h_ring) + (kTcBN + kTcBN / 8 + (cols == 128 ? half : 2)) * 4;  // their minimum
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * cols);
+            long long dbg_epi_wait = 0, dbg_epi_drain = 0, dbg_epi_hits = 0, dbg_epi_hit_tiles = 0, dbg_epi_load = 0, dbg_big_cyc = 0, dbg_big_cnt = 0, dbg_mid_cyc = 0, dbg_mid_cnt = 0;
+            const long long dbg_e0 = clock64();
+            for (int item = cluster_id; item < nitems; item += nclusters) {
+                const TcItem wi = tc_pair_item(p, item);
+                const int seg = wi.seg, nsg = wi.nsg, qt = 2 * wi.qp + (int)rank;
+                const int tile0 = seg;
+                const int ntiles = (p.tiles_total - seg + nsg - 1) / nsg;
+                // seed the threshold with what earlier segments of the same query already proved: their K'-th best
+                // bounds this query's answer from below, so rows scoring under it cannot matter here either.  The slots
+                // are written by other CTAs of this launch; an unfinished one still reads -inf (memset before launch).
+                const size_t q = (size_t)qt * kTcBM + m;
+                float seed = -INFINITY;
+                for (int s2 = 0; s2 < seg; ++s2)
+                    seed = fmaxf(seed, *(const volatile float*)(p.cand_thr + q * p.nslot + (size_t)s2 * halves + half));
+                list.reset(seed);
+                if (p.debug == 4) list.thr = INFINITY;       // ablation: fast path only
+                int row_base = tile0 * kTcBN + half * cols;
+                for (int t = 0; t < ntiles; ++t, ++acc_it, row_base += nsg * kTcBN) {
+                    const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                    // list maintenance rides on the wait for the next accumulator tile
+                    const long long dbg_w0 = (OSML_TC_COUNTERS && p.counters) ? clock64() : 0;
+                    while (!__all_sync(0xffffffffu, ptx::mbar_try_wait_addr(bar_tmem_full + as * 8, aphase)))
+                        if (list.pending()) list.flush_round();
+                    if ((OSML_TC_COUNTERS && p.counters)) dbg_epi_wait += clock64() - dbg_w0;
+                    ptx::tc_fence_after();
+                    const uint32_t taddr = taddr0 + as * kTcBN;
+                    // the tile's h block in shared memory (landed long ago: it was requested with the operand tiles)
+                    ptx::mbar_wait_addr(bar_h_full + hslot * 8, hphase);
+                    const uint32_t hs = hslot * (kTcHBlock * 4);
+                    bool released = false;
+                    if (p.debug != 1 && p.debug != 3) {
+                        if (KP <= 16 && cols == 128) {
+                            // the thread's whole 128-column share of the tile moves to registers in one go and the
+                            // accumulator stage goes straight back to the MMA: TMEM is held for the load time only, and
+                            // the scan (with its irregular hit handling) gets a full extra tile time of slack
+                            float v0[32], v1[32], v2[32], v3[32];
+                            ptx::tmem_ld_32x32(taddr, v0);
+                            ptx::tmem_ld_32x32(taddr + 32, v1);
+                            ptx::tmem_ld_32x32(taddr + 64, v2);
+                            ptx::tmem_ld_32x32(taddr + 96, v3);
+                            const float hmin = lds_f32(hmin_base + hs);      // min(h) over the thread's 128 columns
                             ptx::tmem_ld_wait();
-                            const bool last = c + 64 >= cols;
-                            if (last) {
-                                ptx::tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty[as], 0);
-                                released = true;
+                            if ((OSML_TC_COUNTERS && p.counters)) dbg_epi_load += clock64() - dbg_w0 - 0;
+                            ptx::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive_cluster_addr(bar_tmem_empty + as * 8);
+                            released = true;
+                            if (p.debug != 2) {
+                                // hot path: one max tree over the 128 raw dot products, one compare against
+                                // thr + min(h), one vote.  (The rows are sorted by h, so min(h) is tight for the whole
+                                // tile and the test rarely fires without a real candidate.)
+                                const float tile_max = fmaxf(fmaxf(tc_max32(v0), tc_max32(v1)), fmaxf(tc_max32(v2), tc_max32(v3)));
+                                if (__any_sync(0xffffffffu, tile_max > list.thr + hmin)) {
+                                    const float4 hm0 = lds_f4(hm_base + hs), hm1 = lds_f4(hm_base + hs + 16),
+                                                 hm2 = lds_f4(hm_base + hs + 32), hm3 = lds_f4(hm_base + hs + 48);
+                                    const uint32_t bits = list.lane_bits(v0, hm0) | (list.lane_bits(v1, hm1) << 4) |
+                                                          (list.lane_bits(v2, hm2) << 8) | (list.lane_bits(v3, hm3) << 12);
+                                    const uint32_t mask = __reduce_or_sync(0xffffffffu, bits);
+                                    const long long dbg_d0 = (OSML_TC_COUNTERS && p.counters) ? clock64() : 0;
+                                    list.template drain<true>(mask, v0, v1, v2, v3, row_base, nullptr, h_base + hs);
+                                    if ((OSML_TC_COUNTERS && p.counters)) {
+                                        const long long dd = clock64() - dbg_d0;
+                                        dbg_epi_drain += dd; dbg_epi_hits += __popc(mask); ++dbg_epi_hit_tiles;
+                                        if (dd > 3000) { dbg_big_cyc += dd; ++dbg_big_cnt; }
+                                        else if (dd > 1000) { dbg_mid_cyc += dd; ++dbg_mid_cnt; }
+                                    }
+                                }
+                            } else if (v0[0] + v1[31] + v2[5] + v3[7] == 12345.678f) list.thr = v0[0];
+                        } else {
+                            // two register buffers; the accumulator stage is handed back to the MMA as soon as the last
+                            // TMEM load has landed, the last two chunks are scanned after the release
+                            float va[32], vb[32];
+                            ptx::tmem_ld_32x32(taddr, va);
+                            ptx::tmem_ld_32x32(taddr + 32, vb);
+                            for (int c = 0; c < cols; c += 64) {
+                                const float4 ha = lds_f4(hm_base + hs + (c >> 1)), hb = lds_f4(hm_base + hs + (c >> 1) + 16);
+                                ptx::tmem_ld_wait();
+                                const bool last = c + 64 >= cols;
+                                if (last) {
+                                    ptx::tc_fence_before();
+                                    __syncwarp();
+                                    if (lane == 0) ptx::mbar_arrive_cluster_addr(bar_tmem_empty + as * 8);
+                                    released = true;
+                                }
+                                if (p.debug != 2) list.template scan<true>(va, row_base + c, ha, nullptr, h_base + hs + c * 4);
+                                else if (va[0] + va[31] == 12345.678f) list.thr = va[0];
+                                if (!last) ptx::tmem_ld_32x32(taddr + c + 64, va);
+                                if (p.debug != 2) list.template scan<true>(vb, row_base + c + 32, hb, nullptr, h_base + hs + (c + 32) * 4);
+                                else if (vb[0] + vb[31] == 12345.678f) list.thr = vb[0];
+                                if (!last) ptx::tmem_ld_32x32(taddr + c + 96, vb);
                             }
-                            if (p.debug != 2) list.scan(va, row_base + c);
-                            else if (va[0] + va[31] == 12345.678f) list.thr = va[0];
-                            if (!last) ptx::tmem_ld_32x32(taddr + c + 64, va);
-                            if (p.debug != 2) list.scan(vb, row_base + c + 32);
-                            else if (vb[0] + vb[31] == 12345.678f) list.thr = vb[0];
-                            if (!last) ptx::tmem_ld_32x32(taddr + c + 96, vb);
-                        }
-                    } else {
-                        for (int c = 0; c < cols; c += 32) {
-                            float va[32];
-                            ptx::tmem_ld_32x32(taddr + c, va);
-                            ptx::tmem_ld_wait();
-                            list.scan(va, row_base + c);
                         }
                     }
-                }
-                if (!released) {
-                    ptx::tc_fence_before();
+                    if (!released) {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive_cluster_addr(bar_tmem_empty + as * 8);
+                    }
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty[as], 0);
+                    if (lane == 0) ptx::mbar_arrive_addr(bar_h_empty + hslot * 8);
+                    if (++hslot == (uint32_t)kTcHSlots) { hslot = 0; hphase ^= 1; }
                 }
+                list.flush();
+                const size_t slot = (size_t)seg * halves + half;
+                float* ov = p.cand_val + (q * p.nslot + slot) * KP;
+                int* oi = p.cand_idx + (q * p.nslot + slot) * KP;
+                bool full = true;
+    #pragma unroll
+                for (int e = 0; e < KP; ++e) { ov[e] = list.lv[e]; oi[e] = list.lr[e]; full = full && list.lr[e] >= 0; }
+                // everything this slot dropped scores <= thr (placeholders keep thr at the seed while the list is not full)
+                p.cand_thr[q * p.nslot + slot] = (full || seed > -INFINITY) ? list.thr : -INFINITY;
             }
-            const size_t slot = (size_t)seg * halves + half;
-            float* ov = p.cand_val + (q * p.nslot + slot) * KP;
-            int* oi = p.cand_idx + (q * p.nslot + slot) * KP;
-            bool full = true;
-#pragma unroll
-            for (int e = 0; e < KP; ++e) { ov[e] = list.lv[e]; oi[e] = list.lr[e]; full = full && list.lr[e] >= 0; }
-            // everything this slot dropped scores <= thr (placeholders keep thr at the seed while the list is not full)
-            p.cand_thr[q * p.nslot + slot] = (full || seed > -INFINITY) ? list.thr : -INFINITY;
+            if ((OSML_TC_COUNTERS && p.counters) && lane == 0) {
+                atomicAdd(p.dbg + 3, (unsigned long long)dbg_epi_wait);
+                atomicAdd(p.dbg + 4, (unsigned long long)dbg_epi_drain);
+                atomicAdd(p.dbg + 5, (unsigned long long)dbg_epi_hits);
+                atomicAdd(p.dbg + 6, (unsigned long long)dbg_epi_hit_tiles);
+                atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - dbg_e0));
+                atomicAdd(p.dbg + 8, (unsigned long long)dbg_epi_load);
+                atomicAdd(p.dbg + 9, (unsigned long long)dbg_big_cyc);
+                atomicAdd(p.dbg + 10, (unsigned long long)dbg_big_cnt);
+                atomicAdd(p.dbg + 11, (unsigned long long)dbg_mid_cyc);
+                atomicAdd(p.dbg + 12, (unsigned long long)dbg_mid_cnt);
+            }
         }
     }
     ptx::tc_fence_before();
@@ -766,7 +1058,8 @@ __device__ __forceinline__ float tc_exact_distance(const float* __restrict__ t, 
 __global__ void __launch_bounds__(32 * kRescoreWarps)
 knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __restrict__ queries, int d, int sum_order,
                    int64_t q_count, int ksel, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
-                   const float* __restrict__ cand_thr, int nslot, int kprime, const double* __restrict__ qnorm2,
+                   const float* __restrict__ cand_thr, const int* __restrict__ perm, int64_t npad, int nslot,
+                   int64_t q_single, int slots_single, int kprime, const double* __restrict__ qnorm2,
                    const double* __restrict__ qerr, TcBounds bounds, int64_t index_base, float* __restrict__ out_d,
                    int64_t* __restrict__ out_i, int* __restrict__ flags) {
     __shared__ float s_acc[kRescoreWarps][kTcMaxCand];
@@ -776,9 +1069,11 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * kRescoreWarps + warp;
     if (q >= q_count) return;
+    const float* cv = cand_val + (size_t)q * nslot * kprime;
+    const int* ci = cand_idx + (size_t)q * nslot * kprime;
+    const float* ct = cand_thr + (size_t)q * nslot;
+    if (q < q_single) nslot = slots_single;           // this query was swept in one item: only its first slots exist
     const int ncand = nslot * kprime;
-    const float* cv = cand_val + (size_t)q * ncand;
-    const int* ci = cand_idx + (size_t)q * ncand;
     const float* qrow = queries + (size_t)q * d;
     float* acc = s_acc[warp];
     float* dist = s_dist[warp];
@@ -794,8 +1089,9 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
 
     int nvalid = 0;
     for (int c = lane; c < ncand; c += 32) {
-        const int row = ci[c];
-        const bool valid = row >= 0 && row < n;       // negative: empty slot; >= n: a padding row of the filter copy
+        const int pos = ci[c];                        // position in the (norm-sorted) filter copy; negative: empty slot
+        const int row = (pos >= 0 && pos < npad) ? perm[pos] : -1;        // train row; -1 for padding positions
+        const bool valid = row >= 0 && row < n;
         idx[c] = valid ? row : kIdxSentinel;
         acc[c] = valid ? cv[c] : -INFINITY;
         dist[c] = nan_of<float>();                    // "not computed": sorts after everything
@@ -853,7 +1149,7 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
     if (ok) {
         const double dk = (double)s_best[warp] * (1.0 + 9.5367431640625e-07);   // (k+1)-th exact distance, 2^-20 margin
         for (int s = lane; s < nslot; s += 32) {
-            const float thr = cand_thr[(size_t)q * nslot + s];
+            const float thr = ct[s];
             if (thr == -INFINITY) continue;   // the slot never filled its list: nothing was dropped
             if (!(lower(thr) > dk)) ok = false;    // also catches NaN
         }
@@ -911,8 +1207,23 @@ struct TensorState {
     bool usable = false;          // false if the train set has non-finite rows (then only K2 is exact)
     int64_t npad = 0; int dp = 0;
     double et_max = 0.0, tnorm_max = 0.0;
-    TcBuffer train_bf16, center, stats, partial;
-    TcBuffer q_bf16, q_norm2, q_err, cand_val, cand_idx, cand_thr, flags, fb_list, fb_count, fb_queries, fb_d, fb_i;
+    TcBuffer train_bf16, half_norm, hmin8, hblk, perm, center, stats, partial;
+    TcBuffer dbg;
+    // per-call scratch; level 0 = the caller's queries, level 1 = the retry of the few queries K3 could not prove
+    struct Scratch {
+        TcBuffer q_bf16, q_norm2, q_err, cand_val, cand_idx, cand_thr, flags, fb_list, fb_count, fb_queries, fb_d, fb_i;
+        size_t bytes() const {
+            return q_bf16.cap + q_norm2.cap + q_err.cap + cand_val.cap + cand_idx.cap + cand_thr.cap + flags.cap +
+                   fb_list.cap + fb_count.cap + fb_queries.cap + fb_d.cap + fb_i.cap;
+        }
+        void release() {
+            for (TcBuffer* b : {&q_bf16, &q_norm2, &q_err, &cand_val, &cand_idx, &cand_thr, &flags, &fb_list, &fb_count,
+                                &fb_queries, &fb_d, &fb_i})
+                b->release();
+        }
+    };
+    Scratch scratch[2];
+    int64_t retry_queries = 0;    // queries that went through the level-1 retry since the last reset
     CUtensorMap map_b;
     CUtensorMap map_b_half;   // 128-row boxes for the CTA-pair kernel
     void* encode_fn = nullptr;
@@ -930,6 +1241,7 @@ struct TensorLaunch {
     int opt_smem_lists = 0;  // 1 = force the shared-memory list epilogue
     int opt_cta_group = 0;   // 0 = auto, 1 = single CTA per item, 2 = CTA pairs (cta_group::2)
     int debug = 0;
+    int counters = 0;        // 1 = the CTA-pair kernel records where its issuer / epilogue warps wait (printed to stderr)
 };
 
 using DirectFallback = std::function<int(const void*, int64_t, void*, int64_t*)>;
@@ -956,15 +1268,15 @@ inline bool tensor_path_supported(int dtype, int64_t n, int64_t d, int k) {
 }
 
 inline size_t tensor_bytes(const TensorState& s) {
-    return s.train_bf16.cap + s.center.cap + s.stats.cap + s.partial.cap + s.q_bf16.cap + s.q_norm2.cap + s.q_err.cap +
-           s.cand_val.cap + s.cand_idx.cap + s.cand_thr.cap + s.flags.cap + s.fb_list.cap + s.fb_count.cap + s.fb_queries.cap +
-           s.fb_d.cap + s.fb_i.cap;
+    return s.train_bf16.cap + s.half_norm.cap + s.hmin8.cap + s.hblk.cap + s.perm.cap + s.center.cap + s.stats.cap +
+           s.partial.cap + s.scratch[0].bytes() + s.scratch[1].bytes();
 }
 
 inline void tensor_release(TensorState& s) {
-    for (TcBuffer* b : {&s.train_bf16, &s.center, &s.stats, &s.partial, &s.q_bf16, &s.q_norm2, &s.q_err, &s.cand_val,
-                        &s.cand_idx, &s.cand_thr, &s.flags, &s.fb_list, &s.fb_count, &s.fb_queries, &s.fb_d, &s.fb_i})
+    for (TcBuffer* b : {&s.dbg, &s.train_bf16, &s.half_norm, &s.hmin8, &s.hblk, &s.perm, &s.center, &s.stats, &s.partial})
         b->release();
+    s.scratch[0].release();
+    s.scratch[1].release();
     if (s.ev_k1_begin) cudaEventDestroy(s.ev_k1_begin);
     if (s.ev_k1_end) cudaEventDestroy(s.ev_k1_end);
     s.ev_k1_begin = s.ev_k1_end = nullptr;
@@ -1016,7 +1328,7 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
         return 2;
     }
     const int d = (int)tl.d;
-    st.dp = (d + 3 + kTcKB - 1) / kTcKB * kTcKB;
+    st.dp = (d + kTcKB - 1) / kTcKB * kTcKB;
     st.npad = (tl.n + kTcBN - 1) / kTcBN * kTcBN;
     const float* train = static_cast<const float*>(tl.train);
     const int rows_per_block = 2048;
@@ -1030,12 +1342,34 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
                                                                     st.partial.as<double>());
     tc_col_mean_kernel<<<(d + 127) / 128, 128, 0, stream>>>(st.partial.as<double>(), nblocks, d, tl.n,
                                                             st.center.as<float>());
-    const int64_t threads = st.npad * 32;
-    tc_prep_rows_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
-        train, tl.n, st.npad, d, st.dp, st.center.as<float>(), st.train_bf16.as<__nv_bfloat16>(), nullptr, nullptr,
-        st.stats.as<TcPrepStats>());
-    *launches += 3;
-    TC_TRY(cudaGetLastError());
+    TC_TRY(st.half_norm.reserve((size_t)st.npad * sizeof(float)));
+    TC_TRY(st.hmin8.reserve((size_t)(st.npad / 8) * sizeof(float)));
+    TC_TRY(st.hblk.reserve((size_t)(st.npad / kTcBN) * kTcHBlock * sizeof(float)));
+    TC_TRY(st.perm.reserve((size_t)st.npad * sizeof(int)));
+    {
+        // sort the rows by h = 0.5*|t^|^2 (fit-time only; CUB radix sort of (key, row id) pairs)
+        TcBuffer keys_in, vals_in, temp;
+        TC_TRY(keys_in.reserve((size_t)tl.n * sizeof(float)));
+        TC_TRY(vals_in.reserve((size_t)tl.n * sizeof(int)));
+        tc_train_norms_kernel<<<(unsigned)((tl.n * 32 + 255) / 256), 256, 0, stream>>>(
+            train, tl.n, d, st.center.as<float>(), keys_in.as<float>(), vals_in.as<int>(), st.stats.as<TcPrepStats>());
+        size_t temp_bytes = 0;
+        TC_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in.as<float>(), st.half_norm.as<float>(),
+                                               vals_in.as<int>(), st.perm.as<int>(), (int)tl.n, 0, 32, stream));
+        TC_TRY(temp.reserve(temp_bytes));
+        TC_TRY(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, keys_in.as<float>(), st.half_norm.as<float>(),
+                                               vals_in.as<int>(), st.perm.as<int>(), (int)tl.n, 0, 32, stream));
+        const int64_t threads = st.npad * 32;
+        tc_prep_rows_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+            train, tl.n, st.npad, d, st.dp, st.center.as<float>(), st.perm.as<int>(), st.train_bf16.as<__nv_bfloat16>(),
+            nullptr, nullptr, st.half_norm.as<float>(), st.perm.as<int>());
+        tc_hblock_kernel<<<(unsigned)((st.npad / 8 + 255) / 256), 256, 0, stream>>>(
+            st.half_norm.as<float>(), st.npad, st.hmin8.as<float>(), st.hblk.as<float>());
+        *launches += 6;
+        TC_TRY(cudaGetLastError());
+        TC_TRY(cudaStreamSynchronize(stream));
+        keys_in.release(); vals_in.release(); temp.release();
+    }
     TcPrepStats hs;
     TC_TRY(cudaMemcpyAsync(&hs, st.stats.ptr, sizeof(hs), cudaMemcpyDeviceToHost, stream));
     TC_TRY(cudaStreamSynchronize(stream));
@@ -1059,7 +1393,8 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
 // neighbour search for one block of queries (device, row-major fp32).  out_d/out_i: [q][k+1] final lists.
 inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
                                float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
-                               int64_t* launches, std::string* err, const DirectFallback& direct) {
+                               int64_t* launches, std::string* err, const DirectFallback& direct, int level = 0) {
+    TensorState::Scratch& sc = st.scratch[level];
     const int d = (int)tl.d;
     const int ksel = tl.k + 1;
     const int kprime = tc_kprime(tl.k, tl.slack);
@@ -1071,126 +1406,169 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     // CTA pairs (cta_group::2) need register lists (no shared-memory list code in that kernel)
     // (the pair kernel stages whole half-tiles; for wide rows that no longer fits twice, so use single CTAs there)
     const size_t pair_stage = (size_t)(st.dp / kTcKB) * kTcBHalfBytes;
-    const bool pair_fits = (size_t)st.smem_optin >= (size_t)(st.dp / kTcKB) * kTcABlockBytes + 2 * pair_stage + 1280;
+    const size_t pair_extra = (size_t)kTcHSlots * kTcHBlock * 4 + 256;     // h ring + its barriers (pair kernel only)
+    const bool pair_fits = (size_t)st.smem_optin >=
+        (size_t)(st.dp / kTcKB) * kTcABlockBytes + 2 * pair_stage + (size_t)kTcBufCap * 8 * 32 * 8 + pair_extra + 1280;
     const int tc_cta_group = (reg_lists && tl.opt_cta_group != 1 && pair_fits) ? 2 : 1;
     const int64_t qtile = (int64_t)kTcBM * tc_cta_group;
     const int64_t qpad = (q + qtile - 1) / qtile * qtile;
     const int nqt = (int)(qpad / kTcBM);
     const int tiles_total = (int)(st.npad / kTcBN);
     const int nkb = st.dp / kTcKB;
-    const int ksteps = (d + 3 + 15) / 16;
+    const int ksteps = (d + 15) / 16;
 
-    // every extra segment restarts the per-query threshold (more list inserts, more candidates for K3), so use the
-    // fewest that still give every SM an item; with more query tiles than SMs a single sweep per tile is best
-    int max_seg_by_cand = std::max(1, kTcMaxCand / (kprime * halves));
-    int nseg = 1;
-    {
-        // work items = nqt * nseg over sm_count persistent CTAs: pick the split with the least idle tail, charging
-        // 1 % per extra segment (later segments start from the thresholds earlier ones proved, so they are cheap)
+    // Work split.  Every extra segment restarts the per-query lists (more warm-up, more candidates for K3), so a query
+    // tile is swept in ONE item whenever that keeps the machine busy: with U persistent units and T query tiles, the
+    // first floor(T / U) * U tiles are single-item sweeps and only the remainder -- which would otherwise occupy a
+    // fraction of the machine for a whole sweep -- is cut into nseg interleaved segments.  (Single-CTA kernels split
+    // every tile the same way: nq_single = 0.)
+    const int max_seg_by_cand = std::max(1, kTcMaxCand / (kprime * halves));
+    const int max_seg = std::max(1, std::min(max_seg_by_cand, std::max(1, tiles_total / 8)));
+    const int units = std::max(1, st.sm_count / tc_cta_group);
+    const int nq_units = nqt / tc_cta_group;                 // query tiles (single CTA) or tile pairs
+    int nseg = 1, nq_single = 0;
+    if (tl.opt_nseg > 0) {
+        nseg = std::min(tl.opt_nseg, max_seg);
+    } else {
+        const int rem = tc_cta_group == 2 ? nq_units % units : nq_units;     // units of work left for the split part
+        nq_single = nq_units - rem;
         double best = 1e30;
-        const int units = std::max(1, st.sm_count / tc_cta_group);
-        for (int cand = 1; cand <= 32; ++cand) {
-            const double items = (double)(nqt / tc_cta_group) * cand;
-            const double cost = std::ceil(items / units) / (items / units) + 0.01 * (cand - 1);
+        for (int cand = 1; cand <= max_seg && rem > 0; ++cand) {
+            const double cost = std::ceil((double)rem * cand / units) / cand + 0.01 * (cand - 1);
             if (cost < best - 1e-9) { best = cost; nseg = cand; }
         }
+        if (nseg == 1) nq_single = tc_cta_group == 2 ? nq_units : 0;         // nothing gained by splitting
     }
-    if (tl.opt_nseg > 0) nseg = tl.opt_nseg;
-    nseg = std::max(1, std::min(nseg, std::min(max_seg_by_cand, std::max(1, tiles_total / 8))));
-    int tiles_per_seg = (tiles_total + nseg - 1) / nseg;
-    nseg = (tiles_total + tiles_per_seg - 1) / tiles_per_seg;
+    const int tiles_per_seg = (tiles_total + nseg - 1) / nseg;
     const int nslot = nseg * halves;
 
-    const size_t list_bytes = reg_lists ? 0 : (size_t)kprime * epi_warps * 32 * 8;
+    const size_t list_bytes = reg_lists ? (size_t)kTcBufCap * epi_warps * 32 * 8 : (size_t)kprime * epi_warps * 32 * 8;
     // the query tile stays resident when it leaves room for at least two ring stages; wide rows stream it instead
     const bool a_resident = tc_cta_group == 2 ||
         (size_t)st.smem_optin >= (size_t)nkb * kTcABlockBytes + list_bytes + 2 * (size_t)kTcBStageBytes + 1280;
     const size_t a_bytes = a_resident ? (size_t)nkb * kTcABlockBytes : 0;
     const size_t stage_bytes = tc_cta_group == 2 ? (size_t)nkb * kTcBHalfBytes
                                : (a_resident ? (size_t)kTcBStageBytes : (size_t)kTcABlockBytes + kTcBStageBytes);
-    const size_t fixed = a_bytes + list_bytes + 256 + 1024;
+    const size_t extra = tc_cta_group == 2 ? pair_extra : 0;
+    const size_t fixed = a_bytes + list_bytes + extra + 256 + 1024;
     int stages = (int)(((size_t)st.smem_optin - fixed) / stage_bytes);
     stages = std::min(stages, tc_cta_group == 2 ? 8 : 6);
     if (stages < 2) { if (err) *err = "not enough shared memory for the tensor filter"; return 4; }
-    const size_t smem = a_bytes + (size_t)stages * stage_bytes + list_bytes + 256;
+    const size_t smem = a_bytes + (size_t)stages * stage_bytes + list_bytes + extra + 256;
 
-    TC_TRY(st.q_bf16.reserve((size_t)qpad * st.dp * sizeof(__nv_bfloat16)));
-    TC_TRY(st.q_norm2.reserve((size_t)qpad * sizeof(double)));
-    TC_TRY(st.q_err.reserve((size_t)qpad * sizeof(double)));
-    TC_TRY(st.cand_val.reserve((size_t)qpad * nslot * kprime * sizeof(float)));
-    TC_TRY(st.cand_idx.reserve((size_t)qpad * nslot * kprime * sizeof(int)));
-    TC_TRY(st.cand_thr.reserve((size_t)qpad * nslot * sizeof(float)));
-    TC_TRY(st.flags.reserve((size_t)q * sizeof(int)));
-    TC_TRY(st.fb_list.reserve((size_t)q * sizeof(int)));
-    TC_TRY(st.fb_count.reserve(sizeof(int)));
+    TC_TRY(sc.q_bf16.reserve((size_t)qpad * st.dp * sizeof(__nv_bfloat16)));
+    TC_TRY(sc.q_norm2.reserve((size_t)qpad * sizeof(double)));
+    TC_TRY(sc.q_err.reserve((size_t)qpad * sizeof(double)));
+    TC_TRY(sc.cand_val.reserve((size_t)qpad * nslot * kprime * sizeof(float)));
+    TC_TRY(sc.cand_idx.reserve((size_t)qpad * nslot * kprime * sizeof(int)));
+    TC_TRY(sc.cand_thr.reserve((size_t)qpad * nslot * sizeof(float)));
+    TC_TRY(sc.flags.reserve((size_t)q * sizeof(int)));
+    TC_TRY(sc.fb_list.reserve((size_t)q * sizeof(int)));
+    TC_TRY(sc.fb_count.reserve(sizeof(int)));
 
     const int64_t threads = qpad * 32;
     tc_prep_rows_kernel<false><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
-        d_queries, q, qpad, d, st.dp, st.center.as<float>(), st.q_bf16.as<__nv_bfloat16>(), st.q_norm2.as<double>(),
-        st.q_err.as<double>(), nullptr);
+        d_queries, q, qpad, d, st.dp, st.center.as<float>(), nullptr, sc.q_bf16.as<__nv_bfloat16>(),
+        sc.q_norm2.as<double>(), sc.q_err.as<double>(), nullptr, nullptr);
     ++*launches;
     TC_TRY(cudaGetLastError());
 
     CUtensorMap map_a;
-    int rc = tc_make_map(st, &map_a, st.q_bf16.ptr, qpad, st.dp, kTcBM, err);
+    int rc = tc_make_map(st, &map_a, sc.q_bf16.ptr, qpad, st.dp, kTcBM, err);
     if (rc) return rc;
 
     TcParams p;
-    p.nkb = nkb; p.ksteps = ksteps; p.nqt = nqt; p.nseg = nseg; p.tiles_per_seg = tiles_per_seg;
+    p.nkb = nkb; p.ksteps = ksteps; p.nqt = nqt; p.nseg = nseg; p.nq_single = nq_single; p.tiles_per_seg = tiles_per_seg;
     p.tiles_total = tiles_total; p.kprime = kprime; p.epi_warps = epi_warps; p.stages = stages; p.nslot = nslot; p.a_resident = a_resident ? 1 : 0;
-    p.cand_val = st.cand_val.as<float>(); p.cand_idx = st.cand_idx.as<int>();
-    p.cand_thr = st.cand_thr.as<float>();
+    p.cand_val = sc.cand_val.as<float>(); p.cand_idx = sc.cand_idx.as<int>();
+    p.cand_thr = sc.cand_thr.as<float>();
+    p.h = st.half_norm.as<float>(); p.hmin8 = st.hmin8.as<float>(); p.hblk = st.hblk.as<float>();
     p.debug = tl.debug;
+    p.counters = tl.counters;
+    p.dbg = nullptr;
+    if (tl.counters) {
+        TC_TRY(st.dbg.reserve(16 * sizeof(unsigned long long)));
+        TC_TRY(cudaMemsetAsync(st.dbg.ptr, 0, 16 * sizeof(unsigned long long), stream));
+        p.dbg = st.dbg.as<unsigned long long>();
+    }
     auto kernel = !reg_lists ? knn_tc_filter_kernel<0> : (kprime == 16 ? knn_tc_filter_kernel<16> : knn_tc_filter_kernel<32>);
     if (tc_cta_group == 2) kernel = kprime == 16 ? knn_tc_filter_pair_kernel<16> : knn_tc_filter_pair_kernel<32>;
     TC_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int nitems = (nqt / tc_cta_group) * nseg;
+    const int nitems = nq_single + (nq_units - nq_single) * nseg;
     const int grid = tc_cta_group * std::min(nitems, st.sm_count / tc_cta_group);
     if (!st.ev_k1_begin) { TC_TRY(cudaEventCreate(&st.ev_k1_begin)); TC_TRY(cudaEventCreate(&st.ev_k1_end)); }
-    TC_TRY(cudaMemsetAsync(st.cand_thr.ptr, 0xFF, (size_t)qpad * nslot * sizeof(float), stream));   // NaN bits: "not written"
-    TC_TRY(cudaEventRecord(st.ev_k1_begin, stream));
+    TC_TRY(cudaMemsetAsync(sc.cand_thr.ptr, 0xFF, (size_t)qpad * nslot * sizeof(float), stream));   // NaN bits: "not written"
+    if (level == 0) TC_TRY(cudaEventRecord(st.ev_k1_begin, stream));
     kernel<<<grid, kTcThreads, smem, stream>>>(map_a, tc_cta_group == 2 ? st.map_b_half : st.map_b, p);
-    TC_TRY(cudaEventRecord(st.ev_k1_end, stream));
+    if (level == 0) TC_TRY(cudaEventRecord(st.ev_k1_end, stream));
     ++*launches;
-    ++st.filter_launches;
+    if (level == 0) ++st.filter_launches;
     TC_TRY(cudaGetLastError());
+    if (tl.counters) {      // cycle counters of the CTA-pair kernel (sums over MMA issuers / epilogue warps)
+        unsigned long long h[16];
+        TC_TRY(cudaMemcpyAsync(h, st.dbg.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        TC_TRY(cudaStreamSynchronize(stream));
+        const double issuers = grid / 2.0, ewarps = (double)grid * epi_warps;
+        fprintf(stderr, "[K1 dbg] issuer: total %.0f cyc, wait accumulator %.1f%%, wait operands %.1f%% | epilogue warp: total %.0f cyc, "
+                        "wait tile %.1f%%, wait+load %.1f%%, drain %.1f%%, hit groups/tile %.3f, tiles with hits %.1f%%, drain cyc/hit tile %.0f\n",
+                h[2] / issuers, 100.0 * h[0] / h[2], 100.0 * h[1] / h[2], h[7] / ewarps, 100.0 * h[3] / h[7], 100.0 * h[8] / h[7],
+                100.0 * h[4] / h[7], (double)h[5] / ((double)tiles_total * (nqt / tc_cta_group) * 2 * epi_warps),
+                100.0 * h[6] / ((double)tiles_total * (nqt / tc_cta_group) * 2 * epi_warps), (double)h[4] / std::max(1ull, h[6]));
+        fprintf(stderr, "[K1 dbg] drains: %llu total, %llu > 3000 cyc (%.1f%% of drain time, mean %.0f), %llu in 1000..3000 (%.1f%%, mean %.0f), "
+                        "rest mean %.0f\n", h[6], h[10], 100.0 * h[9] / std::max(1ull, h[4]), (double)h[9] / std::max(1ull, h[10]), h[12],
+                100.0 * h[11] / std::max(1ull, h[4]), (double)h[11] / std::max(1ull, h[12]),
+                (double)(h[4] - h[9] - h[11]) / std::max(1ull, h[6] - h[10] - h[12]));
+    }
     if (tl.debug) return 0;   // profiling ablations: results are meaningless, skip rescoring
 
     TcBounds b;
     b.et_max = st.et_max; b.tnorm_max = st.tnorm_max;
-    // (K + 8) * 2^-22 accumulation + 2^-23 norm split + 2^-17 for the index bits packed into list values
-    b.c_mma = (double)(ksteps * 16 + 8) * 2.384185791015625e-07 + 1.2e-7 + 7.62939453125e-06;
+    // (K + 8) * 2^-22 accumulation + 2^-22 for rounding h, subtracting it and the group test thr + min(h) +
+    // 2^-17 for the slot bits packed into list values
+    b.c_mma = (double)(ksteps * 16 + 8) * 2.384185791015625e-07 + 2.4e-7 + 7.62939453125e-06;
     b.gamma = (double)(d + 4) * 1.1920928955078125e-07;                      // (D + 4) * 2^-23
-    TC_TRY(cudaMemsetAsync(st.fb_count.ptr, 0, sizeof(int), stream));
+    TC_TRY(cudaMemsetAsync(sc.fb_count.ptr, 0, sizeof(int), stream));
     knn_rescore_kernel<<<(unsigned)((q + kRescoreWarps - 1) / kRescoreWarps), 32 * kRescoreWarps, 0, stream>>>(
-        static_cast<const float*>(tl.train), tl.n, d_queries, d, tl.sum_order, q, ksel, st.cand_val.as<float>(),
-        st.cand_idx.as<int>(), st.cand_thr.as<float>(), nslot, kprime, st.q_norm2.as<double>(), st.q_err.as<double>(), b, tl.index_base, out_d,
-        out_i, st.flags.as<int>());
-    tc_compact_flags_kernel<<<(unsigned)((q + 255) / 256), 256, 0, stream>>>(st.flags.as<int>(), q, st.fb_list.as<int>(),
-                                                                             st.fb_count.as<int>());
+        static_cast<const float*>(tl.train), tl.n, d_queries, d, tl.sum_order, q, ksel, sc.cand_val.as<float>(),
+        sc.cand_idx.as<int>(), sc.cand_thr.as<float>(), st.perm.as<int>(), st.npad, nslot,
+        (int64_t)nq_single * kTcBM * tc_cta_group, halves, kprime, sc.q_norm2.as<double>(), sc.q_err.as<double>(), b, tl.index_base, out_d,
+        out_i, sc.flags.as<int>());
+    tc_compact_flags_kernel<<<(unsigned)((q + 255) / 256), 256, 0, stream>>>(sc.flags.as<int>(), q, sc.fb_list.as<int>(),
+                                                                             sc.fb_count.as<int>());
     *launches += 2;
     TC_TRY(cudaGetLastError());
     int count = 0;
-    TC_TRY(cudaMemcpyAsync(&count, st.fb_count.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    TC_TRY(cudaMemcpyAsync(&count, sc.fb_count.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
     TC_TRY(cudaStreamSynchronize(stream));
-    {
+    if (level == 0) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, st.ev_k1_begin, st.ev_k1_end) == cudaSuccess) st.filter_ms += ms;
     }
     if (count > 0) {
-        TC_TRY(st.fb_queries.reserve((size_t)count * d * sizeof(float)));
-        TC_TRY(st.fb_d.reserve((size_t)count * ksel * sizeof(float)));
-        TC_TRY(st.fb_i.reserve((size_t)count * ksel * sizeof(int64_t)));
-        tc_gather_rows_kernel<<<count, 128, 0, stream>>>(d_queries, st.fb_list.as<int>(), count, d,
-                                                         st.fb_queries.as<float>());
+        TC_TRY(sc.fb_queries.reserve((size_t)count * d * sizeof(float)));
+        TC_TRY(sc.fb_d.reserve((size_t)count * ksel * sizeof(float)));
+        TC_TRY(sc.fb_i.reserve((size_t)count * ksel * sizeof(int64_t)));
+        tc_gather_rows_kernel<<<count, 128, 0, stream>>>(d_queries, sc.fb_list.as<int>(), count, d,
+                                                         sc.fb_queries.as<float>());
         ++*launches;
-        rc = direct(st.fb_queries.ptr, count, st.fb_d.ptr, st.fb_i.as<int64_t>());
+        if (level == 0 && !tl.debug) {
+            // second chance on the filter: the same kernels over the few unproven queries, cut into as many train
+            // segments as K3 can take -- every (segment, half) slot keeps its own K' best, so the kept set reaches
+            // many times deeper and the proof almost always goes through.  Whatever still fails goes to K2 from there.
+            TensorLaunch retry = tl;
+            retry.opt_nseg = 1 << 20;                  // clamped to the maximum
+            rc = tc_neighbours_block(st, retry, sc.fb_queries.as<float>(), count, sc.fb_d.as<float>(),
+                                     sc.fb_i.as<int64_t>(), stream, fallback, launches, err, direct, 1);
+            st.retry_queries += count;
+        } else {
+            rc = direct(sc.fb_queries.ptr, count, sc.fb_d.ptr, sc.fb_i.as<int64_t>());
+            *fallback += count;
+        }
         if (rc) return rc;
-        tc_scatter_lists_kernel<<<count, 64, 0, stream>>>(st.fb_d.as<float>(), st.fb_i.as<int64_t>(),
-                                                          st.fb_list.as<int>(), count, ksel, out_d, out_i);
+        tc_scatter_lists_kernel<<<count, 64, 0, stream>>>(sc.fb_d.as<float>(), sc.fb_i.as<int64_t>(),
+                                                          sc.fb_list.as<int>(), count, ksel, out_d, out_i);
         ++*launches;
         TC_TRY(cudaGetLastError());
-        *fallback += count;
     }
     return 0;
 }
