@@ -1054,7 +1054,15 @@ __device__ __forceinline__ float tc_exact_distance(const float* __restrict__ t, 
 
 // One warp per query.  Exact distances are only computed where they can matter: first for the k+1 candidates with the
 // best filter score, whose largest exact distance D0 caps the answer; any other candidate whose score-derived lower
-// bound already exceeds D0 cannot be among the k+1 nearest and is never gathered from HBM.
+// bound already exceeds D0 cannot be among the k+1 nearest and is never gathered from HBM.  Work is kept proportional
+// to the candidates that matter (a few dozen) even when many (segment, half) slots feed the query: the k+1 best scores
+// are picked by k+1 warp arg-max rounds, and everything after that runs on compacted lists.
+__device__ __forceinline__ unsigned long long tc_score_key(float a, int c) {
+    uint32_t u = __float_as_uint(a);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);            // order-preserving map of float to unsigned
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)c);   // ties: lowest position
+}
+
 __global__ void __launch_bounds__(32 * kRescoreWarps)
 knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __restrict__ queries, int d, int sum_order,
                    int64_t q_count, int ksel, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
@@ -1063,8 +1071,9 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
                    const double* __restrict__ qerr, TcBounds bounds, int64_t index_base, float* __restrict__ out_d,
                    int64_t* __restrict__ out_i, int* __restrict__ flags) {
     __shared__ float s_acc[kRescoreWarps][kTcMaxCand];
-    __shared__ float s_dist[kRescoreWarps][kTcMaxCand];
     __shared__ int s_idx[kRescoreWarps][kTcMaxCand];
+    __shared__ float s_dist[kRescoreWarps][kTcMaxCand];       // exact distances, by position in s_work
+    __shared__ short s_work[kRescoreWarps][kTcMaxCand];       // compacted candidate positions: selected, then the rest
     __shared__ float s_best[kRescoreWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * kRescoreWarps + warp;
@@ -1078,6 +1087,7 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
     float* acc = s_acc[warp];
     float* dist = s_dist[warp];
     int* idx = s_idx[warp];
+    short* work = s_work[warp];
 
     const double n2 = qnorm2[q], eq = qerr[q];
     const double eps = bounds.c_mma * (sqrt(n2) * bounds.tnorm_max + 0.5 * bounds.tnorm_max * bounds.tnorm_max);
@@ -1094,55 +1104,64 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
         const bool valid = row >= 0 && row < n;
         idx[c] = valid ? row : kIdxSentinel;
         acc[c] = valid ? cv[c] : -INFINITY;
-        dist[c] = nan_of<float>();                    // "not computed": sorts after everything
         nvalid += valid ? 1 : 0;
     }
     for (int off = 16; off > 0; off >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, off);
     __syncwarp();
     bool ok = nvalid >= ksel;
-    // pass 1: the k+1 best-scoring candidates (selection first, then the gathers, so ranks see a stable score array)
-    uint32_t selected = 0;                            // bit i: candidate lane + 32 * i
-    for (int c = lane, i = 0; c < ncand; c += 32, ++i) {
-        if (idx[c] == kIdxSentinel) continue;
-        const float ac = acc[c];
-        int rank = 0;
-        for (int o = 0; o < ncand; ++o) {
-            const float ao = acc[o];
-            rank += (ao > ac || (ao == ac && o < c)) ? 1 : 0;
+    // pass 1: the k+1 best-scoring candidates, one warp arg-max round each (ncand <= 512: 16 entries per lane)
+    uint32_t taken = 0;                               // bit i: candidate lane + 32 * i already picked
+    const int nsel = min(ksel, nvalid);
+    for (int s = 0; s < nsel; ++s) {
+        unsigned long long best = 0ull;
+        for (int c = lane, i = 0; c < ncand; c += 32, ++i) {
+            if (((taken >> i) & 1u) || idx[c] == kIdxSentinel) continue;
+            const unsigned long long key = tc_score_key(acc[c], c);
+            best = key > best ? key : best;
         }
-        if (rank < ksel) selected |= 1u << i;
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+            best = o > best ? o : best;
+        }
+        const int c = (int)(0xFFFFFFFFu - (uint32_t)best);
+        if ((c & 31) == lane) taken |= 1u << (c >> 5);
+        if (lane == 0) work[s] = (short)c;
     }
+    __syncwarp();
     float d0 = 0.0f;
     bool d0_nan = false;
-    for (int c = lane, i = 0; c < ncand; c += 32, ++i) {
-        if (!((selected >> i) & 1u)) continue;
-        const float dc = tc_exact_distance(train + (size_t)idx[c] * d, qrow, d, sum_order);
-        dist[c] = dc;
+    for (int j = lane; j < nsel; j += 32) {
+        const float dc = tc_exact_distance(train + (size_t)idx[work[j]] * d, qrow, d, sum_order);
+        dist[j] = dc;
         d0 = fmaxf(d0, dc);
         d0_nan = d0_nan || dc != dc;
     }
     for (int off = 16; off > 0; off >>= 1) d0 = fmaxf(d0, __shfl_xor_sync(0xffffffffu, d0, off));
     d0_nan = __any_sync(0xffffffffu, d0_nan) || !ok;
     const double cap = d0_nan ? (double)INFINITY : (double)d0 * (1.0 + 9.5367431640625e-07);
-    __syncwarp();
-    // pass 2: whatever the cap cannot rule out
-    for (int c = lane; c < ncand; c += 32) {
-        if (idx[c] == kIdxSentinel || dist[c] == dist[c]) continue;         // empty, or already computed in pass 1
-        if (lower(acc[c]) > cap) { idx[c] = kIdxSentinel; continue; }       // provably beyond the (k+1)-th nearest
-        dist[c] = tc_exact_distance(train + (size_t)idx[c] * d, qrow, d, sum_order);
+    // pass 2: whatever the cap cannot rule out, compacted so that the gathers are spread over the lanes
+    int m = nsel;
+    for (int c0 = 0, i = 0; c0 < ncand; c0 += 32, ++i) {
+        const int c = c0 + lane;
+        const bool need = c < ncand && !((taken >> i) & 1u) && idx[c] != kIdxSentinel && !(lower(acc[c]) > cap);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, need);
+        if (need) work[m + __popc(ballot & ((1u << lane) - 1u))] = (short)c;
+        m += __popc(ballot);
     }
     __syncwarp();
-    // rank the computed candidates by (distance, index); keys are unique because the slots cover disjoint row ranges
-    for (int c = lane; c < ncand; c += 32) {
-        const int ic = idx[c];
-        if (ic == kIdxSentinel) continue;
-        const float dc = dist[c];
+    for (int j = nsel + lane; j < m; j += 32)
+        dist[j] = tc_exact_distance(train + (size_t)idx[work[j]] * d, qrow, d, sum_order);
+    __syncwarp();
+    // rank the computed candidates by (distance, index); keys are unique because the slots cover disjoint row sets
+    for (int j = lane; j < m; j += 32) {
+        const float dj = dist[j];
+        const int ij = idx[work[j]];
         int rank = 0;
-        for (int o = 0; o < ncand; ++o) rank += (idx[o] != kIdxSentinel && key_less(dist[o], idx[o], dc, ic)) ? 1 : 0;
+        for (int o = 0; o < m; ++o) rank += key_less(dist[o], idx[work[o]], dj, ij) ? 1 : 0;
         if (rank < ksel) {
-            out_d[q * ksel + rank] = dc;
-            out_i[q * ksel + rank] = index_base + ic;
-            if (rank == ksel - 1) s_best[warp] = dc;
+            out_d[q * ksel + rank] = dj;
+            out_i[q * ksel + rank] = index_base + ij;
+            if (rank == ksel - 1) s_best[warp] = dj;
         }
     }
     __syncwarp();
