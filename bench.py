@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the kNN predict hot path (BASELINE.json metric: kNN predict queries/sec, k=10, on B200).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3|c5]
 
 Workload (default, BASELINE.json configs[3], "C4"): synthetic 1,000,000 x 128 fp32 train set resident on every GPU,
 100,000 fp32 queries per GPU per step, k = 10, classification labels in 0..9 -- the reference's
@@ -16,6 +16,11 @@ One step = one pass of the hot path over one batch of 100,000 queries:
          over its CUDA-event duration, against the measured dense bf16 peak of MEASURED_PEAKS.json
   cpu_baseline  the oracle port of the reference's numpy path on a bounded sample of the same queries, 1 core
 `--impl reference` times that CPU port with every host core it can use and prints the same JSON shape.
+
+`--workload c5` (BASELINE.json configs[4] shape, not the headline line): train rows SHARDED across the GPUs, 2,500,000 x 96
+fp32 rows per GPU (20M x 96 at 8 GPUs), every GPU searches the same 131,072 queries per step (a subset of the config's
+1M, stated in `config`), k = 32; the per-GPU exact partial lists are exchanged with one NCCL all-gather and merged
+(osml_b200/sharded.py).
 """
 import argparse
 import json
@@ -36,6 +41,7 @@ WORKLOADS = {
     'c3': (60_000, 784, 10_000, 10, 3),
 }
 METRIC = 'kNN predict queries/sec (k=10)'
+C5 = {'rows_per_gpu': 2_500_000, 'd': 96, 'q': 131_072, 'k': 32, 'seed': 5}
 
 
 def make_data(name, rank):
@@ -328,15 +334,135 @@ def run_ours(args):
     return 0
 
 
+def run_ours_c5(args):
+    """Train-sharded mode: rows split across ranks, one NCCL all-gather of the exact partial
+    (k+1)-lists per step, exact merge on every rank."""
+    import torch
+    import torch.distributed as dist
+    from osml_b200 import _native, sharded
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    rows, d, q, k, seed = C5['rows_per_gpu'], C5['d'], C5['q'], C5['k'], C5['seed']
+    n_total = rows * world
+    shard = np.asfortranarray(np.random.default_rng(seed + 100 * rank).standard_normal((rows, d), dtype=np.float32))
+    labels = np.random.default_rng(seed).integers(0, 10, n_total)
+    queries = np.random.default_rng(seed + 1).standard_normal((q, d), dtype=np.float32)     # the same on every rank
+    ix = sharded.TrainShardedIndex(shard, labels, k, device=local_rank, shard_of=(rank * rows, n_total), path=args.path)
+    index = ix.backend.index
+    d_queries = torch.from_numpy(queries).cuda()
+    pinned_q = torch.from_numpy(queries).pin_memory().numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        return ix.predict(d_queries, _native.CLASSIFICATION, keep_on_device=True)
+
+    def e2e_step():
+        return ix.predict(pinned_q, _native.CLASSIFICATION)
+
+    def timed(step_fn, steps, use_events):
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        filt_ms, filt_launches = 0.0, 0
+        for _ in range(steps):
+            step_fn()
+            st = index.stats()
+            filt_ms += st['last_filter_ms']
+            filt_launches += st['last_filter_launches']
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) if use_events else (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), filt_ms, filt_launches
+
+    for _ in range(max(args.warmup, 3)):
+        first_pred = resident_step()
+    torch.cuda.synchronize()
+    first_pred = first_pred.cpu().numpy().copy()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    index.reset_stats()
+    total_ms, filt_ms, filt_launches = timed(resident_step, args.steps, True)
+    stats = index.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        e2e_step()
+    e2e_ms, _, _ = timed(e2e_step, args.steps, False)
+    assert np.array_equal(e2e_step(), first_pred), 'host-buffer and device-buffer paths disagree'
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peak_tflops, peak_gbs, peak_kind = load_peaks()
+    k1_ms = filt_ms / max(filt_launches, 1)
+    flop_per_launch = 2.0 * rows * d * q * args.steps / max(filt_launches, 1)
+    achieved = flop_per_launch / (k1_ms / 1e3) / 1e12 if k1_ms > 0 else None
+    # CPU port: the full train set of this run is rank 0's shard only when world == 1; otherwise check a sample of
+    # queries against rank 0's rows is meaningless, so the port is timed on rank 0's shard as its own problem
+    sample = 4
+    t0 = time.perf_counter()
+    from oracle import knn_oracle as ko
+    cpu_pred = ko.predict_classification(shard, labels[:rows], queries[:sample], k=k, tie_rule='reference')
+    cpu_dt = time.perf_counter() - t0
+    line = {'metric': 'kNN predict queries/sec (k=32), train-sharded', 'value': q * args.steps / (total_ms / 1e3),
+            'unit': 'queries/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'C5 shape: synthetic gaussian %d x %d fp32 train rows, %d per GPU (train-sharded x%d), '
+                                   '%d fp32 queries per step on every GPU (subset of the config\'s 1M), k=%d, '
+                                   'KNearestNeighborsClassification' % (n_total, d, rows, world, q, k),
+                       'train_rows': n_total, 'features': d, 'queries_per_step': q, 'k': k,
+                       'parallelism': 'train-sharded x%d, one NCCL all-gather of %d bytes per rank per step'
+                                      % (world, q * (k + 1) * 12),
+                       'l2': 'inputs larger than L2: %.0f MB bf16 filter copy per GPU vs 126 MB L2' % (rows * 128 * 2 / 1e6)},
+            'e2e': {'value': q * args.steps / (e2e_ms / 1e3), 'unit': 'queries/s', 'h2d_bytes_per_step': int(queries.nbytes),
+                    'd2h_bytes_per_step': int(q * 8), 'ms_per_step': e2e_ms / args.steps,
+                    'api': 'osml_b200.sharded.TrainShardedIndex.predict (host queries -> neighbours -> all-gather -> merge)'},
+            'gpu_launches': int(stats['kernel_launches']),
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
+                         'frac': achieved / peak_tflops if achieved else None, 'traffic': None,
+                         'kernel': 'knn_tc_filter_pair_kernel<32>', 'kernel_ms_per_launch': k1_ms,
+                         'launches_timed': filt_launches, 'kernel_share_of_step': filt_ms / total_ms,
+                         'algorithmic_flop_per_launch': flop_per_launch, 'peak_source': peak_kind + ' bf16 dense, sustained'},
+            'cpu_baseline': {'value': sample / cpu_dt, 'unit': 'queries/s', 'cores': 1, 'kind': 'port',
+                             'sample': '%d queries against one %d-row shard through the numpy oracle port' % (sample, rows),
+                             'matches_gpu_predictions': bool(np.array_equal(cpu_pred, first_pred[:sample])) if world == 1 else None},
+            'clocks': clocks, 'retry_queries_per_step': stats['retry_queries'] / args.steps,
+            'fallback_queries_per_step': stats['fallback_queries'] / args.steps, 'path': args.path}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS) + ['c5'])
     ap.add_argument('--path', default='auto', choices=['auto', 'direct', 'tensor'])
     args = ap.parse_args()
+    if args.workload == 'c5':
+        if args.impl == 'reference':
+            print(json.dumps({'impl': 'reference', 'unavailable': 'the reference arm is timed on the headline '
+                                                                  'workload (c4) only'}))
+            return 0
+        return run_ours_c5(args)
     if args.impl == 'reference':
         return run_reference_arm(args)
     return run_ours(args)

@@ -52,17 +52,21 @@ class NativeBackend:
         self.dist_dtype = torch.float32 if self.index.dist_dtype == np.float32 else torch.float64
 
     def neighbours(self, queries):
+        """queries: host (Q, D) array, or a contiguous CUDA tensor already on this device."""
         torch = self.torch
         q = queries.shape[0]
         with torch.cuda.device(self.device):
-            d_q = torch.from_numpy(np.ascontiguousarray(queries)).to(self.device)
+            if isinstance(queries, torch.Tensor):
+                d_q = queries
+            else:
+                d_q = torch.from_numpy(np.ascontiguousarray(queries)).to(self.device)
             idx = torch.empty((q, self.k + 1), dtype=torch.int64, device=self.device)
             dist = torch.empty((q, self.k + 1), dtype=self.dist_dtype, device=self.device)
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self.index.neighbours_device(d_q.data_ptr(), q, idx.data_ptr(), dist.data_ptr(), stream)
         return idx, dist
 
-    def merge_predict(self, parts_idx, parts_dist, task):
+    def merge_predict(self, parts_idx, parts_dist, task, keep_on_device=False):
         torch = self.torch
         parts, q = parts_idx.shape[0], parts_idx.shape[1]
         with torch.cuda.device(self.device):
@@ -70,7 +74,7 @@ class NativeBackend:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self.index.merge_predict_device(parts_idx.data_ptr(), parts_dist.data_ptr(), parts, q, task,
                                             pred.data_ptr(), None, None, stream)
-            return pred.cpu().numpy()
+            return pred if keep_on_device else pred.cpu().numpy()
 
     def close(self):
         self.index.close()
@@ -80,20 +84,29 @@ class TrainShardedIndex:
     """Train rows sharded across the ranks of `group`; predictions bit-identical to the unsharded index."""
 
     def __init__(self, train, labels, k, rbf_gamma=1, epsilon=1e-8, device=None, group=None, backend_factory=None,
-                 query_block=131072, path='auto'):
+                 query_block=131072, path='auto', shard_of=None):
+        """`train` is the whole (N, D) matrix (every rank slices its block), or -- with shard_of=(lo, N) -- this rank's
+        rows [lo, lo + len(train)) of a matrix of N rows that no single process has to hold.  `labels` always has N
+        entries."""
         train = np.asarray(train)
         self.world, self.rank = _world(group)
         self.group = group
-        self.n = train.shape[0]
+        self.n = train.shape[0] if shard_of is None else int(shard_of[1])
         self.k = int(k)
         if self.n < self.k + 1:
             raise ValueError                                  # predict.py:768-769 on the *global* row count
-        self.bounds = split_bounds(self.n, self.world)
-        lo, hi = self.bounds[self.rank]
-        if hi <= lo:
-            raise ValueError('rank %d would hold no training rows' % self.rank)
         sum_order = _native.sum_order_of(train)               # layout of the whole matrix decides the order
-        shard = train[lo:hi]
+        if shard_of is None:
+            self.bounds = split_bounds(self.n, self.world)
+            lo, hi = self.bounds[self.rank]
+            if hi <= lo:
+                raise ValueError('rank %d would hold no training rows' % self.rank)
+            shard = train[lo:hi]
+        else:
+            lo = int(shard_of[0])
+            shard = train
+            if len(labels) != self.n or lo < 0 or lo + shard.shape[0] > self.n:
+                raise ValueError
         if device is None:
             from osml_b200.predict import _default_device
             device = _default_device()
@@ -102,12 +115,16 @@ class TrainShardedIndex:
                                path)
         self.query_block = int(query_block)
 
-    def predict(self, queries, task):
-        """queries: the same (Q, D) matrix on every rank.  Returns the fp64 predictions for all Q on every rank."""
-        queries = np.asarray(queries)
+    def predict(self, queries, task, keep_on_device=False):
+        """queries: the same (Q, D) matrix on every rank (host array, or a CUDA tensor on this rank's device).
+        Returns the fp64 predictions for all Q on every rank (a CUDA tensor with keep_on_device)."""
+        on_device = not isinstance(queries, np.ndarray) and hasattr(queries, 'data_ptr')
+        if not on_device:
+            queries = np.asarray(queries)
         if self.n < self.k + 2:
             raise ValueError                                  # np.argpartition(d, k + 1) needs k + 1 < N
-        out = np.empty(queries.shape[0], dtype=np.float64)
+        outs = []
+        out = None if keep_on_device else np.empty(queries.shape[0], dtype=np.float64)
         for q0 in range(0, queries.shape[0], self.query_block):
             block = queries[q0:q0 + self.query_block]
             idx, dist_ = self.backend.neighbours(block)
@@ -123,7 +140,13 @@ class TrainShardedIndex:
                 all_dist = all_dist.view(self.world, qb, ksel)
             else:
                 all_idx, all_dist = idx[None], dist_[None]
-            out[q0:q0 + block.shape[0]] = self.backend.merge_predict(all_idx, all_dist, task)
+            if keep_on_device:
+                outs.append(self.backend.merge_predict(all_idx, all_dist, task, keep_on_device=True))
+            else:
+                out[q0:q0 + block.shape[0]] = self.backend.merge_predict(all_idx, all_dist, task)
+        if keep_on_device:
+            import torch
+            return outs[0] if len(outs) == 1 else torch.cat(outs)
         return out
 
     def close(self):
