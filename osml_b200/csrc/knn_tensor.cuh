@@ -51,7 +51,7 @@ constexpr int kTcBN = 256;            // train rows per tile (UMMA N)
 constexpr int kTcKB = 64;             // bf16 per K block = one 128-byte swizzled row
 constexpr int kTcABlockBytes = kTcBM * 128;   // 16 KB
 constexpr int kTcBStageBytes = kTcBN * 128;   // 32 KB
-constexpr int kTcThreads = 384;       // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int kTcThreads = 384;       // warp 0 TMA, 1 MMA (3 too in the pair kernel), 2 TMEM alloc, 4..11 epilogue
 constexpr int kTcMaxKPrime = 64;
 constexpr int kTcMaxCand = 512;       // candidates per query K3 handles (slots * K')
 
@@ -307,11 +307,14 @@ __device__ __forceinline__ void lds_v2(uint32_t addr, uint32_t& a, uint32_t& b) 
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
 }
 
-template <int KP>
+// kSmemRows: the row indices of the entries live in shared memory ([KP][threads] ints) instead of registers -- the
+// pair kernel with K' = 32 needs the registers to stage a whole tile share (128 values) next to the 32 list values.
+template <int KP, bool kSmemRows = false>
 struct TcRegList {
     static constexpr uint32_t kSlotMask = KP - 1;
     float lv[KP];
-    int lr[KP];
+    int lr[kSmemRows ? 1 : KP];
+    uint32_t rows_addr, rows_stride;   // kSmemRows: shared address of this thread's entry 0, bytes between entries
     float thr;
     uint32_t buf_addr;     // shared-memory address of this thread's buffer entry 0
     uint32_t buf_stride;   // bytes between consecutive entries of one thread (= epilogue threads * 8)
@@ -325,7 +328,11 @@ struct TcRegList {
     __device__ __forceinline__ void reset(float seed = -INFINITY) {
         const uint32_t base = seed > -3.0e38f ? __float_as_uint(seed) : 0xFF7FFFFFu;
 #pragma unroll
-        for (int e = 0; e < KP; ++e) { lv[e] = __uint_as_float((base & ~kSlotMask) | (uint32_t)e); lr[e] = -1; }
+        for (int e = 0; e < KP; ++e) {
+            lv[e] = __uint_as_float((base & ~kSlotMask) | (uint32_t)e);
+            if (kSmemRows) sts_b32(rows_addr + (uint32_t)e * rows_stride, 0xffffffffu);
+            else lr[e] = -1;
+        }
         thr = tc_list_min<KP>(lv);
         cnt = 0;
         rd = 0;
@@ -334,14 +341,28 @@ struct TcRegList {
     __device__ __forceinline__ void insert_sel(bool take, float cur, int row) {
         const uint32_t slot = take ? (__float_as_uint(thr) & kSlotMask) : 0xFFFFFFFFu;
         const uint32_t nvb = (__float_as_uint(cur) & ~kSlotMask) | (slot & kSlotMask);
+        if (kSmemRows) {
+            if (take) sts_b32(rows_addr + (slot & kSlotMask) * rows_stride, (uint32_t)row);
 #pragma unroll
-        for (int e = 0; e < KP; ++e) {
-            uint32_t vb = __float_as_uint(lv[e]);
-            asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, %3;\n\tselp.b32 %0, %4, %0, p;\n\tselp.b32 %1, %5, %1, p;\n\t}"
-                : "+r"(vb), "+r"(lr[e]) : "r"(slot), "r"((uint32_t)e), "r"(nvb), "r"(row));
-            lv[e] = __uint_as_float(vb);
+            for (int e = 0; e < KP; ++e) {
+                uint32_t vb = __float_as_uint(lv[e]);
+                asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\tselp.b32 %0, %3, %0, p;\n\t}"
+                    : "+r"(vb) : "r"(slot), "r"((uint32_t)e), "r"(nvb));
+                lv[e] = __uint_as_float(vb);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < KP; ++e) {
+                uint32_t vb = __float_as_uint(lv[e]);
+                asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, %3;\n\tselp.b32 %0, %4, %0, p;\n\tselp.b32 %1, %5, %1, p;\n\t}"
+                    : "+r"(vb), "+r"(lr[e]) : "r"(slot), "r"((uint32_t)e), "r"(nvb), "r"(row));
+                lv[e] = __uint_as_float(vb);
+            }
         }
         thr = tc_list_min<KP>(lv);
+    }
+    __device__ __forceinline__ int row_of(int e) const {
+        return kSmemRows ? (int)__float_as_uint(lds_f32(rows_addr + (uint32_t)e * rows_stride)) : lr[kSmemRows ? 0 : e];
     }
     // warp-collective: every lane with unread buffer entries feeds its oldest one to its list.  Callers run rounds
     // while they wait for the next accumulator tile, so list maintenance rides on otherwise idle issue slots.
@@ -625,7 +646,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 int* oi = p.cand_idx + (q * p.nslot + slot) * KP;
                 bool full = true;
 #pragma unroll
-                for (int e = 0; e < KP; ++e) { ov[e] = list.lv[e]; oi[e] = list.lr[e]; full = full && list.lr[e] >= 0; }
+                for (int e = 0; e < KP; ++e) { const int r = list.row_of(e); ov[e] = list.lv[e]; oi[e] = r; full = full && r >= 0; }
                 p.cand_thr[q * p.nslot + slot] = full ? list.thr : -INFINITY;
             }
         } else {
@@ -737,7 +758,8 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     const int epi_threads = p.epi_warps * 32;
     unsigned char* cand_buf = b_smem + (size_t)p.stages * stage_bytes;         // [kTcBufCap][epi_threads] x 8 B
     unsigned char* h_ring = cand_buf + (size_t)kTcBufCap * epi_threads * 8;     // [kTcHSlots][kTcHBlock] floats
-    uint64_t* bars = reinterpret_cast<uint64_t*>(h_ring + (size_t)kTcHSlots * kTcHBlock * 4);
+    unsigned char* row_lists = h_ring + (size_t)kTcHSlots * kTcHBlock * 4;     // K' > 16: [K'][epi_threads] ints
+    uint64_t* bars = reinterpret_cast<uint64_t*>(row_lists + (KP > 16 ? (size_t)KP * epi_threads * 4 : 0));
     uint64_t* full_bar = bars;                    // [stages]  (used in the leader)
     uint64_t* empty_bar = bars + 8;               // [stages]
     uint64_t* tmem_full = bars + 16;              // [2]
@@ -763,7 +785,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 2 * p.epi_warps); }
         ptx::mbar_init(a_full, 2);
-        ptx::mbar_init(a_empty, 1);
+        ptx::mbar_init(a_empty, 2);
         for (int s = 0; s < kTcHSlots; ++s) { ptx::mbar_init(&h_full[s], 1); ptx::mbar_init(&h_empty[s], p.epi_warps); }
         ptx::fence_barrier_init();
     }
@@ -813,14 +835,20 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     }
                 }
             }
-        } else if (warp == 1) {
+        } else if (warp == 1 || warp == 3) {
             if (lane == 0 && leader) {
-                // ===== MMA issuer (leader CTA only) =====
+                // ===== MMA issuers (leader CTA only) =====
+                // Two threads, one per accumulator stage: issuer 0 (warp 1) takes the even tiles, issuer 1 (warp 3) the
+                // odd ones.  The tensor pipe holds only a couple of MMAs in flight, so a single issuer's per-tile
+                // bookkeeping (two barrier waits, two commits: ~400 cycles) showed up as pipe bubbles; with two, one
+                // thread waits and commits while the other keeps the pipe fed.  Tiles of different parity write
+                // different TMEM stages and read different shared-memory stages, so their relative order is free.
+                const uint32_t issuer = (uint32_t)warp >> 1;
                 const uint32_t idesc = ptx::umma_idesc_bf16(2 * kTcBM, kTcBN);
                 const uint32_t hi = ptx::umma_desc_hi_k_sw128();
                 const uint32_t a_lo0 = ptx::umma_desc_lo(ptx::smem_u32(a_smem)), b_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_smem));
                 uint32_t stage = 0, phase = 0, it = 0, acc_it = 0;
-                long long dbg_wait_acc = 0, dbg_wait_ops = 0;
+                long long dbg_wait_acc = 0, dbg_wait_ops = 0, dbg_issue = 0, dbg_commit = 0, dbg_t2 = 0;
                 const long long dbg_t0 = clock64();
                 for (int item = cluster_id; item < nitems; item += nclusters, ++it) {
                     const TcItem wi = tc_pair_item(p, item);
@@ -829,13 +857,17 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     ptx::tc_fence_after();
                     for (int t = 0; t < ntiles; ++t, ++acc_it) {
                         const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                        if (as != issuer) {                          // the other issuer's tile
+                            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         if ((OSML_TC_COUNTERS && p.counters)) {      // where does the issuer wait: accumulator stage (epilogue) or operands (TMA)?
                             const long long t0 = clock64();
                             ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
                             const long long t1 = clock64();
                             ptx::mbar_wait(&full_bar[stage], phase);
                             const long long t2 = clock64();
-                            dbg_wait_acc += t1 - t0; dbg_wait_ops += t2 - t1;
+                            dbg_wait_acc += t1 - t0; dbg_wait_ops += t2 - t1; dbg_t2 = t2;
                         } else {
                             ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
                             ptx::mbar_wait(&full_bar[stage], phase);
@@ -853,16 +885,20 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                                     ptx::umma_bf16_ss_pair_lohi(tmem_d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc,
                                                                 (uint32_t)((kb | ks) != 0));
                         }
+                        const long long dbg_t3 = (OSML_TC_COUNTERS && p.counters) ? clock64() : 0;
                         ptx::umma_commit_pair(&empty_bar[stage]);      // both CTAs may refill this stage
                         ptx::umma_commit_pair(&tmem_full[as]);         // both CTAs' epilogues may read the tile
+                        if ((OSML_TC_COUNTERS && p.counters)) { const long long t4 = clock64(); dbg_commit += t4 - dbg_t3; dbg_issue += dbg_t3 - dbg_t2; }
                         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                     }
-                    ptx::umma_commit_pair(a_empty);
+                    ptx::umma_commit_pair(a_empty);                  // one arrival per issuer: all MMAs on the query tile retired
                 }
-                if ((OSML_TC_COUNTERS && p.counters)) {
+                if ((OSML_TC_COUNTERS && p.counters) && issuer == 0) {
                     atomicAdd(p.dbg + 0, (unsigned long long)dbg_wait_acc);
                     atomicAdd(p.dbg + 1, (unsigned long long)dbg_wait_ops);
                     atomicAdd(p.dbg + 2, (unsigned long long)(clock64() - dbg_t0));
+                    atomicAdd(p.dbg + 13, (unsigned long long)dbg_issue);
+                    atomicAdd(p.dbg + 14, (unsigned long long)dbg_commit);
                 }
             }
         }
@@ -875,7 +911,10 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const int cols = kTcBN / halves;
             const int m = quarter * 32 + lane;
             uint32_t acc_it = 0, hslot = 0, hphase = 0;
-            TcRegList<KP> list;
+            constexpr bool kSmemRows = KP > 16;
+            TcRegList<KP, kSmemRows> list;
+            list.rows_addr = ptx::smem_u32(row_lists) + (uint32_t)(ew * 32 + lane) * 4u;
+            list.rows_stride = (uint32_t)epi_threads * 4u;
             list.attach(ptx::smem_u32(cand_buf) + (uint32_t)(ew * 32 + lane) * 8u, (uint32_t)epi_threads * 8u);
             // loop-invariant shared-memory addresses, kept in registers
             const uint32_t bar_tmem_full = ptx::smem_u32(tmem_full);                          // + 8 * stage
@@ -916,7 +955,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     const uint32_t hs = hslot * (kTcHBlock * 4);
                     bool released = false;
                     if (p.debug != 1 && p.debug != 3) {
-                        if (KP <= 16 && cols == 128) {
+                        if (cols == 128) {
                             // the thread's whole 128-column share of the tile moves to registers in one go and the
                             // accumulator stage goes straight back to the MMA: TMEM is held for the load time only, and
                             // the scan (with its irregular hit handling) gets a full extra tile time of slack
@@ -993,7 +1032,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 int* oi = p.cand_idx + (q * p.nslot + slot) * KP;
                 bool full = true;
     #pragma unroll
-                for (int e = 0; e < KP; ++e) { ov[e] = list.lv[e]; oi[e] = list.lr[e]; full = full && list.lr[e] >= 0; }
+                for (int e = 0; e < KP; ++e) { const int r = list.row_of(e); ov[e] = list.lv[e]; oi[e] = r; full = full && r >= 0; }
                 // everything this slot dropped scores <= thr (placeholders keep thr at the seed while the list is not full)
                 p.cand_thr[q * p.nslot + slot] = (full || seed > -INFINITY) ? list.thr : -INFINITY;
             }
@@ -1425,7 +1464,8 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     // CTA pairs (cta_group::2) need register lists (no shared-memory list code in that kernel)
     // (the pair kernel stages whole half-tiles; for wide rows that no longer fits twice, so use single CTAs there)
     const size_t pair_stage = (size_t)(st.dp / kTcKB) * kTcBHalfBytes;
-    const size_t pair_extra = (size_t)kTcHSlots * kTcHBlock * 4 + 256;     // h ring + its barriers (pair kernel only)
+    // pair kernel only: h ring + its barriers, and the lists' row indices when K' = 32
+    const size_t pair_extra = (size_t)kTcHSlots * kTcHBlock * 4 + 256 + (kprime > 16 ? (size_t)kprime * epi_warps * 32 * 4 : 0);
     const bool pair_fits = (size_t)st.smem_optin >=
         (size_t)(st.dp / kTcKB) * kTcABlockBytes + 2 * pair_stage + (size_t)kTcBufCap * 8 * 32 * 8 + pair_extra + 1280;
     const int tc_cta_group = (reg_lists && tl.opt_cta_group != 1 && pair_fits) ? 2 : 1;
@@ -1533,6 +1573,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
                 h[2] / issuers, 100.0 * h[0] / h[2], 100.0 * h[1] / h[2], h[7] / ewarps, 100.0 * h[3] / h[7], 100.0 * h[8] / h[7],
                 100.0 * h[4] / h[7], (double)h[5] / ((double)tiles_total * (nqt / tc_cta_group) * 2 * epi_warps),
                 100.0 * h[6] / ((double)tiles_total * (nqt / tc_cta_group) * 2 * epi_warps), (double)h[4] / std::max(1ull, h[6]));
+        fprintf(stderr, "[K1 dbg] issuer: MMA issue %.1f%%, commits %.1f%%\n", 100.0 * h[13] / h[2], 100.0 * h[14] / h[2]);
         fprintf(stderr, "[K1 dbg] drains: %llu total, %llu > 3000 cyc (%.1f%% of drain time, mean %.0f), %llu in 1000..3000 (%.1f%%, mean %.0f), "
                         "rest mean %.0f\n", h[6], h[10], 100.0 * h[9] / std::max(1ull, h[4]), (double)h[9] / std::max(1ull, h[10]), h[12],
                 100.0 * h[11] / std::max(1ull, h[4]), (double)h[11] / std::max(1ull, h[12]),
