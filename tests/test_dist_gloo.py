@@ -72,6 +72,11 @@ def _worker(rank, world, port, results):
                                            query_block=16)
             assert ix.bounds == [(0, 151), (151, 301)]
             out['train_' + name] = ix.predict(queries, task)
+        # shard-local construction: each rank only passes its own rows (uneven split on purpose)
+        lo, hi = (0, 100) if rank == 0 else (100, n)
+        ix = sharded.TrainShardedIndex(train[lo:hi], labels_c, k, rbf_gamma=0.7, backend_factory=OracleBackend,
+                                       query_block=16, shard_of=(lo, n))
+        out['train_cls_local'] = ix.predict(queries, 1)
         full = ko.predict_classification(train, labels_c, queries, k=k, rbf_gamma=0.7)
 
         def block(lo, hi):
@@ -106,6 +111,7 @@ def test_world_size_2_sharded_paths_match_the_unsharded_oracle():
         got = results[rank]
         assert np.array_equal(got['train_cls'], want_c)
         assert np.array_equal(got['train_reg'], want_r)          # merge is exact: bit-identical to unsharded
+        assert np.array_equal(got['train_cls_local'], want_c)
         assert np.array_equal(got['query'], want_c)
         assert np.array_equal(got['query_tiny'], want_c[:1])
 
@@ -119,3 +125,5 @@ def test_single_process_degenerates_to_one_shard():
     assert np.array_equal(ix.predict(queries, 1), ko.predict_classification(train, labels, queries, k=4))
     with pytest.raises(ValueError):
         sharded.TrainShardedIndex(train[:4], labels[:4], 4, backend_factory=OracleBackend)
+    with pytest.raises(ValueError):                              # labels must cover the whole matrix, not the shard
+        sharded.TrainShardedIndex(train[:20], labels[:20], 4, backend_factory=OracleBackend, shard_of=(10, 50))

@@ -1,4 +1,5 @@
-"""GPU parity of the tcgen05 filter path (K0 + K1 + K3, with K2 for unproven queries) against the oracle.
+"""GPU parity of the tcgen05 filter path (K0 + K1 + K3, a finer second filter pass and finally K2 for unproven
+queries) against the oracle.
 
 The path is exact by construction (completeness proof or fallback), so besides bit-parity these tests assert that the
 filter actually carries the load: the share of queries that had to be re-run on the direct kernel must stay small."""
@@ -11,11 +12,13 @@ from tests import parity
 pytestmark = pytest.mark.gpu
 
 
-def _run(train, labels, test, k, task='classification', gamma=1, slack=None):
+def _run(train, labels, test, k, task='classification', gamma=1, slack=None, segments=None):
     ix = _native.Index(train, labels, k, gamma, 1e-8)
     ix.set_option('path', _native.PATH_TENSOR)
     if slack is not None:
         ix.set_option('slack', slack)
+    if segments is not None:
+        ix.set_option('segments', segments)
     code = _native.REGRESSION if task == 'regression' else _native.CLASSIFICATION
     pred, idx, dist = ix.predict(test, code, return_neighbours=True)
     stats = ix.stats()
@@ -128,3 +131,61 @@ def test_list_length_plans(k):
     pred, idx, dist, stats = _run(train, labels, test, k, task='regression')
     parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'regression')
     assert stats['fallback_queries'] <= 20, stats
+
+
+def test_single_sweep_items_with_a_split_tail():
+    """More query-tile pairs than CTA pairs on the machine: the first full waves are swept in one item each, the
+    remainder is cut into interleaved segments (tc_pair_item).  Bit-identical to the direct kernel."""
+    rng = np.random.default_rng(21)
+    n, d, q, k = 20000, 16, 256 * 80 + 37, 5          # 81 pairs on 74 clusters: 74 single sweeps + 7 split pairs
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = rng.standard_normal((q, d), dtype=np.float32)
+    labels = rng.integers(0, 4, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    ix.set_option('path', _native.PATH_DIRECT)
+    d_pred, d_idx, d_dist = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    ix.close()
+    assert np.array_equal(idx, d_idx) and np.array_equal(dist, d_dist) and np.array_equal(pred, d_pred)
+    assert stats['fallback_queries'] <= q // 50, stats
+
+
+@pytest.mark.parametrize('segments', [1, 2, 5, 16])
+def test_forced_segment_counts(segments):
+    rng = np.random.default_rng(22)
+    n, d, q, k = 70000, 20, 300, 9
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = rng.standard_normal((q, d), dtype=np.float32)
+    labels = rng.integers(0, 4, n)
+    pred, idx, dist, stats = _run(train, labels, test, k, segments=segments)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+    assert stats['fallback_queries'] <= q // 20, stats
+
+
+def test_unproven_queries_take_the_second_filter_pass():
+    """Clustered data: many rows at nearly the same distance make the completeness proof fail on the first pass for some
+    queries; they must come back exact from the finer second pass (retry_queries), not only from the direct kernel."""
+    rng = np.random.default_rng(23)
+    centres = rng.standard_normal((30, 48)).astype(np.float32)
+    train = np.asfortranarray(centres[rng.integers(0, 30, 60000)] +
+                              1e-3 * rng.standard_normal((60000, 48)).astype(np.float32))
+    test = centres[rng.integers(0, 30, 400)] + 1e-3 * rng.standard_normal((400, 48)).astype(np.float32)
+    labels = rng.integers(0, 5, 60000)
+    pred, idx, dist, stats = _run(train, labels, test, 10)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, 10, 1, 'classification')
+    assert stats['retry_queries'] > 0, stats
+
+
+def test_rows_with_very_different_norms():
+    """The filter copy is sorted by row norm and the hot path tests against thr + min(h): rows whose norms span orders
+    of magnitude (and a few all-zero rows) must not disturb exactness."""
+    rng = np.random.default_rng(24)
+    n, d, q, k = 50000, 33, 500, 10
+    scale = np.exp(rng.uniform(-4, 4, (n, 1))).astype(np.float32)
+    train = rng.standard_normal((n, d), dtype=np.float32) * scale
+    train[rng.integers(0, n, 50)] = 0.0
+    train = np.asfortranarray(train)
+    test = rng.standard_normal((q, d), dtype=np.float32) * np.exp(rng.uniform(-3, 3, (q, 1))).astype(np.float32)
+    labels = rng.integers(0, 7, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
