@@ -975,12 +975,18 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                                 // hot path: one max tree over the 128 raw dot products, one compare against
                                 // thr + min(h), one vote.  (The rows are sorted by h, so min(h) is tight for the whole
                                 // tile and the test rarely fires without a real candidate.)
-                                const float tile_max = fmaxf(fmaxf(tc_max32(v0), tc_max32(v1)), fmaxf(tc_max32(v2), tc_max32(v3)));
-                                if (__any_sync(0xffffffffu, tile_max > list.thr + hmin)) {
-                                    const float4 hm0 = lds_f4(hm_base + hs), hm1 = lds_f4(hm_base + hs + 16),
-                                                 hm2 = lds_f4(hm_base + hs + 32), hm3 = lds_f4(hm_base + hs + 48);
-                                    const uint32_t bits = list.lane_bits(v0, hm0) | (list.lane_bits(v1, hm1) << 4) |
-                                                          (list.lane_bits(v2, hm2) << 8) | (list.lane_bits(v3, hm3) << 12);
+                                const float m0 = tc_max32(v0), m1 = tc_max32(v1), m2 = tc_max32(v2), m3 = tc_max32(v3);
+                                const float tile_max = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                                const float bar = list.thr + hmin;
+                                if (__any_sync(0xffffffffu, tile_max > bar)) {
+                                    // which 32-column chunks (warp-uniform), then which groups of 8 inside those only
+                                    const uint32_t cmask = __reduce_or_sync(0xffffffffu, (m0 > bar ? 1u : 0u) | (m1 > bar ? 2u : 0u) |
+                                                                                         (m2 > bar ? 4u : 0u) | (m3 > bar ? 8u : 0u));
+                                    uint32_t bits = 0;
+                                    if (cmask & 1u) bits |= list.lane_bits(v0, lds_f4(hm_base + hs));
+                                    if (cmask & 2u) bits |= list.lane_bits(v1, lds_f4(hm_base + hs + 16)) << 4;
+                                    if (cmask & 4u) bits |= list.lane_bits(v2, lds_f4(hm_base + hs + 32)) << 8;
+                                    if (cmask & 8u) bits |= list.lane_bits(v3, lds_f4(hm_base + hs + 48)) << 12;
                                     const uint32_t mask = __reduce_or_sync(0xffffffffu, bits);
                                     const long long dbg_d0 = (OSML_TC_COUNTERS && p.counters) ? clock64() : 0;
                                     list.template drain<true>(mask, v0, v1, v2, v3, row_base, nullptr, h_base + hs);
