@@ -4,22 +4,26 @@
 // k+1 smallest (predict.py:750).  Doing that arithmetic literally costs 3 un-fusable CUDA-core instructions per
 // element (K2).  Here the tensor cores only *filter*:
 //
-//   K0  knn_prep_rows      one streaming pass: centre by the train column means, round to bf16, record h = 0.5*|t^|^2
-//                          per train row (plus its minimum over every group of 8 rows), |q^|^2 per query and the
-//                          rounding residuals |q^ - (q - c)|.
-//   K1  knn_tc_filter      persistent tcgen05 kernel: score[q][t] = q^ . t^ - h[t] (so |q^ - t^|^2 = |q^|^2 - 2*score)
+//   K0  knn_prep_rows      centre by the train column means, round to bf16, h = 0.5*|t^|^2 per train row; the filter
+//                          copy holds the rows sorted by h (perm maps positions back to train rows) and, per 256-row
+//                          tile, an "h block" (h, its minimum per 8 rows / per half tile).  Per call: the queries'
+//                          bf16 copy, |q^|^2 and the rounding residuals |q^ - (q - c)|.
+//   K1  knn_tc_filter      persistent tcgen05 kernels: score[q][t] = q^ . t^ - h[t] (so |q^ - t^|^2 = |q^|^2 - 2*score)
 //                          with TMA-staged, 128B-swizzled operand tiles and FP32 accumulators in TMEM; the epilogue
 //                          reads each 128 x 256 accumulator tile straight out of TMEM and keeps, per query, the K'
-//                          largest scores per train segment.  The distance matrix never leaves the SM.  The tensor
-//                          core only computes the D-long dot products (K = D, no padding columns for the norms): the
-//                          hot path tests a group of 8 columns against thr + min(h over the group), and only the rare
-//                          groups that pass subtract h element by element.
+//                          largest scores per (train segment, column half).  The distance matrix never leaves the SM.
+//                          The tensor core only computes the D-long dot products (K = D, no padding columns for the
+//                          norms): the hot path compares a max tree over the raw dot products with thr + min(h), and
+//                          only the rare groups of 8 columns that pass subtract h element by element.
+//                            knn_tc_filter_pair_kernel  CTA pairs (cta_group::2), the production kernel for D <= 253
+//                            knn_tc_filter_kernel       one CTA per tile: wide rows, shared-memory lists for k > 21
 //   K3  knn_rescore        per query: exact distances of the candidates in the oracle's arithmetic and summation
 //                          order, top-(k+1) by (distance, index), and a completeness proof -- every row the filter
-//                          dropped has acc <= the segment's K'-th best, which bounds its true distance from below
+//                          dropped has score <= the slot's K'-th best, which bounds its true distance from below
 //                          by sqrt(|q^|^2 - 2*(thr + eps)) - (Eq + Et); if that bound exceeds the exact (k+1)-th
-//                          distance the result equals the brute-force one.  Queries that cannot be proven are
-//                          re-run on K2.  So the output is bit-identical to K2 / the oracle whatever the filter does.
+//                          distance the result equals the brute-force one.  Queries that cannot be proven go through
+//                          a second, finer-grained filter pass and, failing that, K2.  So the output is bit-identical
+//                          to K2 / the oracle whatever the filter does.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
