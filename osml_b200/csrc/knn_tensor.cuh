@@ -435,6 +435,7 @@ struct TcRegList {
     __device__ __forceinline__ void drain(uint32_t mask, const float (&v0)[32], const float (&v1)[32],
                                           const float (&v2)[32], const float (&v3)[32], int row0,
                                           const float* __restrict__ hrow, uint32_t h_saddr) {
+        if (__any_sync(0xffffffffu, cnt > kTcBufCap - 8)) flush();
 #pragma unroll 1
         while (mask != 0) {
             const int g = __ffs((int)mask) - 1;
@@ -449,18 +450,29 @@ struct TcRegList {
             }
             // one statically indexed copy of the 8-element append per group (registers cannot be indexed dynamically,
             // and gathering the group into a common array first costs more than the append itself)
-            switch (g) {
-#define OSML_TC_CASE(G, ARR, OFF) case G: append_group<OFF>(ARR, ha, hb, row0 + 8 * G); break;
-                OSML_TC_CASE(0, v0, 0) OSML_TC_CASE(1, v0, 8) OSML_TC_CASE(2, v0, 16) OSML_TC_CASE(3, v0, 24)
-                OSML_TC_CASE(4, v1, 0) OSML_TC_CASE(5, v1, 8) OSML_TC_CASE(6, v1, 16) OSML_TC_CASE(7, v1, 24)
-                OSML_TC_CASE(8, v2, 0) OSML_TC_CASE(9, v2, 8) OSML_TC_CASE(10, v2, 16) OSML_TC_CASE(11, v2, 24)
-                OSML_TC_CASE(12, v3, 0) OSML_TC_CASE(13, v3, 8) OSML_TC_CASE(14, v3, 16)
-                default: append_group<24>(v3, ha, hb, row0 + 120); break;
-#undef OSML_TC_CASE
+            // (an explicit two-level branch tree on the warp-uniform g: a 16-way jump table costs a constant-bank load)
+#define OSML_TC_QUAD(ARR, BASE)                                                                     \
+            {                                                                                        \
+                const int gq = g & 3;                                                                \
+                if (gq < 2) {                                                                        \
+                    if (gq == 0) append_group<0>(ARR, ha, hb, row0 + 8 * (BASE));                    \
+                    else append_group<8>(ARR, ha, hb, row0 + 8 * (BASE) + 8);                        \
+                } else {                                                                             \
+                    if (gq == 2) append_group<16>(ARR, ha, hb, row0 + 8 * (BASE) + 16);              \
+                    else append_group<24>(ARR, ha, hb, row0 + 8 * (BASE) + 24);                      \
+                }                                                                                    \
             }
+            if (g < 8) {
+                if (g < 4) OSML_TC_QUAD(v0, 0) else OSML_TC_QUAD(v1, 4)
+            } else {
+                if (g < 12) OSML_TC_QUAD(v2, 8) else OSML_TC_QUAD(v3, 12)
+            }
+#undef OSML_TC_QUAD
             // forced catch-up when a buffer nears its capacity (mostly in the first tiles of a sweep, when every
             // value beats the threshold); otherwise the lists catch up while the warp waits for its next tile
-            if (__any_sync(0xffffffffu, cnt > kTcBufCap - 8)) flush();
+            // (a group adds at most 8 entries, and the loop is entered with at most kTcBufCap - 8: no check needed
+            // after the last group)
+            if (mask != 0 && __any_sync(0xffffffffu, cnt > kTcBufCap - 8)) flush();
         }
     }
     // one 32-column chunk starting at train row row0 (hm: the 4 group minima of h)
