@@ -134,6 +134,26 @@ int osml_knn_describe(osml_knn_index* index, int64_t* n, int64_t* d, int* k, int
 /* Message of the last failure on the calling thread ("" if none). */
 const char* osml_knn_last_error(void);
 
+/*
+ * Column transform in front of kNN: Centering (osml/transform.py:53-66, denom == NULL) and Standardization
+ * (osml/transform.py:69-84), out[i][j] = (in[i][j] - shift[j]) / denom[j], in numpy's arithmetic: OSML_KNN_F32 input
+ * gives float32 output, every other dtype float64 output (numpy subtracts a float64 mean from integer data); one
+ * rounding for the subtraction, one for the division.
+ *   in, out      n x d host matrices in the same `layout`; out has the OUTPUT dtype
+ *   shift, denom d elements of the output dtype (mean, and sd + epsilon as numpy rounds it); host pointers
+ * Replaces TransformativeModel._transform (osml/transform.py:64-65, 83-84) for the two classes.
+ */
+int osml_knn_column_transform(int device, const void* in, int dtype, int layout, int64_t n, int64_t d,
+                              const void* shift, const void* denom, void* out);
+
+/*
+ * Fuses the same transform into osml_knn_predict / osml_knn_predict_device: the queries are passed RAW (dtype of the
+ * index, which must be OSML_KNN_F32 or OSML_KNN_F64) and are transformed on the device right after the upload, so
+ * the host pass over Q x D of `standardization.transform(query_df)` disappears.  shift == NULL removes the
+ * transform; denom may be NULL (centering).  The vectors are copied.
+ */
+int osml_knn_set_query_transform(osml_knn_index* ix, const void* shift, const void* denom);
+
 /* ABI version of this header: major * 1000 + minor. */
 int osml_knn_abi_version(void);
 

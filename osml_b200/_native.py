@@ -29,7 +29,7 @@ DTYPE_CODES = {
 SYMBOLS = ('osml_knn_create', 'osml_knn_destroy', 'osml_knn_predict', 'osml_knn_predict_device',
            'osml_knn_neighbours_device', 'osml_knn_merge_predict_device', 'osml_knn_set_option',
            'osml_knn_get_stats', 'osml_knn_reset_stats', 'osml_knn_describe', 'osml_knn_last_error',
-           'osml_knn_abi_version')
+           'osml_knn_abi_version', 'osml_knn_column_transform', 'osml_knn_set_query_transform')
 
 
 class Stats(ctypes.Structure):
@@ -68,6 +68,8 @@ def lib():
     cdll.osml_knn_reset_stats.argtypes = [c_vp]
     cdll.osml_knn_describe.argtypes = [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_int),
                                        ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    cdll.osml_knn_column_transform.argtypes = [c_int, c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_vp]
+    cdll.osml_knn_set_query_transform.argtypes = [c_vp, c_vp, c_vp]
     cdll.osml_knn_last_error.restype = ctypes.c_char_p
     cdll.osml_knn_last_error.argtypes = []
     cdll.osml_knn_abi_version.argtypes = []
@@ -119,6 +121,33 @@ def sum_order_of(values):
     return SUM_SEQUENTIAL if s0 <= s1 else SUM_PAIRWISE
 
 
+def transform_dtype(dtype):
+    """Output dtype of the reference's Centering / Standardization for a frame of `dtype` (numpy promotion rules)."""
+    return np.dtype(np.float32) if np.dtype(dtype) == np.float32 else np.dtype(np.float64)
+
+
+def column_transform(values, shift, denom=None, device=0):
+    """out = (values - shift) / denom per column on the GPU (osml_knn_column_transform); same memory order as
+    ``values``.  ``denom=None``: centering only."""
+    values = np.asarray(values)
+    if values.ndim != 2:
+        raise ValueError
+    mat, layout = matrix_layout(values)
+    out_dtype = transform_dtype(mat.dtype)
+    shift = np.ascontiguousarray(shift, dtype=out_dtype)
+    denom_p = None
+    if denom is not None:
+        denom = np.ascontiguousarray(denom, dtype=out_dtype)
+        denom_p = denom.ctypes.data
+    n, d = mat.shape
+    if shift.shape != (d,) or (denom is not None and denom.shape != (d,)):
+        raise ValueError
+    out = np.empty((n, d), dtype=out_dtype, order='F' if layout == COL_MAJOR else 'C')
+    check(lib().osml_knn_column_transform(int(device), mat.ctypes.data, dtype_code(mat.dtype), layout, int(n), int(d),
+                                          shift.ctypes.data, denom_p, out.ctypes.data))
+    return out
+
+
 class Index:
     """Owner of one ``osml_knn_index`` handle."""
 
@@ -155,6 +184,20 @@ class Index:
 
     def set_option(self, name, value):
         check(lib().osml_knn_set_option(self._handle, name.encode(), float(value)))
+
+    def set_query_transform(self, shift, denom=None):
+        """Queries are passed raw from now on and become (q - shift) / denom on the device (None: remove)."""
+        if shift is None:
+            check(lib().osml_knn_set_query_transform(self._handle, None, None))
+            return
+        shift = np.ascontiguousarray(shift, dtype=self.dtype)
+        denom_p = None
+        if denom is not None:
+            denom = np.ascontiguousarray(denom, dtype=self.dtype)
+            denom_p = denom.ctypes.data
+        if shift.shape != (self.d,) or (denom is not None and denom.shape != (self.d,)):
+            raise ValueError
+        check(lib().osml_knn_set_query_transform(self._handle, shift.ctypes.data, denom_p))
 
     def stats(self):
         st = Stats()

@@ -14,6 +14,7 @@
 #include "knn_common.cuh"
 #include "knn_direct.cuh"
 #include "knn_tensor.cuh"
+#include "knn_transform.cuh"
 
 namespace {
 
@@ -106,6 +107,8 @@ struct osml_knn_index {
     DeviceBuffer part_d, part_i;   // K2 partial lists
     DeviceBuffer nn_d, nn_i;       // final lists
     DeviceBuffer pred;
+    DeviceBuffer q_shift, q_denom;   // fused query transform (osml_knn_set_query_transform), index dtype
+    bool has_q_transform = false, has_q_denom = false;
     osml::TensorState tensor;  // K0/K1/K3 state (bf16 copy, norms, tensor maps, scratch)
 
     cudaStream_t stream = nullptr;
@@ -333,7 +336,7 @@ int check_predict_args(const osml_knn_index* ix, int64_t q) {
 
 extern "C" {
 
-int osml_knn_abi_version(void) { return 1001; }
+int osml_knn_abi_version(void) { return 1002; }
 
 const char* osml_knn_last_error(void) { return g_last_error.c_str(); }
 
@@ -394,6 +397,7 @@ int osml_knn_destroy(osml_knn_index* ix) {
     osml::tensor_release(ix->tensor);
     ix->train.release(); ix->label_bits.release(); ix->stage.release(); ix->queries.release();
     ix->part_d.release(); ix->part_i.release(); ix->nn_d.release(); ix->nn_i.release(); ix->pred.release();
+    ix->q_shift.release(); ix->q_denom.release();
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
     if (ix->ev2) cudaEventDestroy(ix->ev2);
@@ -410,15 +414,56 @@ int osml_knn_neighbours_device(osml_knn_index* ix, const void* d_queries, int64_
     return neighbours(ix, d_queries, q, d_out_dist, d_out_idx, static_cast<cudaStream_t>(stream));
 }
 
+}  // extern "C"
+
+namespace {
+
+// y = (x - shift) / denom on a row-major device matrix of the index dtype (in == out allowed)
+int apply_query_transform(osml_knn_index* ix, const void* d_in, void* d_out, int64_t q, cudaStream_t stream) {
+    const void* denom = ix->has_q_denom ? ix->q_denom.ptr : nullptr;
+    cudaError_t e = ix->dtype == OSML_KNN_F32
+        ? osml::launch_column_transform<float, float>(d_in, d_out, q, ix->d, 0, ix->q_shift.ptr, denom, stream)
+        : osml::launch_column_transform<double, double>(d_in, d_out, q, ix->d, 0, ix->q_shift.ptr, denom, stream);
+    ix->stats.kernel_launches++;
+    if (e != cudaSuccess) return fail(OSML_KNN_ECUDA, cudaGetErrorString(e));
+    return OSML_KNN_OK;
+}
+
+int predict_device_impl(osml_knn_index* ix, const void* d_queries, int64_t q, int task, double* d_out_pred,
+                        int64_t* d_out_idx, void* d_out_dist, cudaStream_t stream);
+
+}  // namespace
+
+extern "C" {
+
 int osml_knn_predict_device(osml_knn_index* ix, const void* d_queries, int64_t q, int task, double* d_out_pred,
                             int64_t* d_out_idx, void* d_out_dist, void* stream_v) {
+    int rc = check_predict_args(ix, q);
+    if (rc != OSML_KNN_OK) return rc;
+    if (!d_queries || !d_out_pred) return fail(OSML_KNN_EINVAL, "null argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (ix->has_q_transform) {            // the caller's buffer stays untouched: transform into the index's copy
+        DeviceGuard guard(ix->device);
+        CUDA_TRY(ix->queries.reserve((size_t)q * ix->d * dtype_size(ix->dtype)));
+        rc = apply_query_transform(ix, d_queries, ix->queries.ptr, q, stream);
+        if (rc != OSML_KNN_OK) return rc;
+        d_queries = ix->queries.ptr;
+    }
+    return predict_device_impl(ix, d_queries, q, task, d_out_pred, d_out_idx, d_out_dist, stream);
+}
+
+}  // extern "C"
+
+namespace {
+
+int predict_device_impl(osml_knn_index* ix, const void* d_queries, int64_t q, int task, double* d_out_pred,
+                        int64_t* d_out_idx, void* d_out_dist, cudaStream_t stream) {
     int rc = check_predict_args(ix, q);
     if (rc != OSML_KNN_OK) return rc;
     if (!d_queries || !d_out_pred) return fail(OSML_KNN_EINVAL, "null argument");
     if (ix->n != ix->n_labels || ix->index_base != 0)
         return fail(OSML_KNN_EINVAL, "index holds a shard: use neighbours + merge_predict");
     DeviceGuard guard(ix->device);
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const size_t ksel = (size_t)ix->ksel();
     void* nn_d = d_out_dist;
     int64_t* nn_i = d_out_idx;
@@ -434,6 +479,10 @@ int osml_knn_predict_device(osml_knn_index* ix, const void* d_queries, int64_t q
     return OSML_KNN_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
 int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_t q, int task, double* out_pred,
                      int64_t* out_idx, void* out_dist) {
     int rc = check_predict_args(ix, q);
@@ -448,8 +497,12 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
     CUDA_TRY(ix->nn_d.reserve((size_t)q * ksel * ix->dist_size()));
     CUDA_TRY(ix->nn_i.reserve((size_t)q * ksel * 8));
     CUDA_TRY(ix->pred.reserve((size_t)q * 8));
-    rc = osml_knn_predict_device(ix, ix->queries.ptr, q, task, ix->pred.as<double>(), ix->nn_i.as<int64_t>(),
-                                 ix->nn_d.ptr, ix->stream);
+    if (ix->has_q_transform) {            // raw queries: Centering / Standardization on the device, in place
+        rc = apply_query_transform(ix, ix->queries.ptr, ix->queries.ptr, q, ix->stream);
+        if (rc != OSML_KNN_OK) return rc;
+    }
+    rc = predict_device_impl(ix, ix->queries.ptr, q, task, ix->pred.as<double>(), ix->nn_i.as<int64_t>(), ix->nn_d.ptr,
+                             ix->stream);
     if (rc != OSML_KNN_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_pred, ix->pred.ptr, (size_t)q * 8, cudaMemcpyDeviceToHost, ix->stream));
     if (out_idx) CUDA_TRY(cudaMemcpyAsync(out_idx, ix->nn_i.ptr, (size_t)q * ksel * 8, cudaMemcpyDeviceToHost, ix->stream));
@@ -494,6 +547,72 @@ int osml_knn_merge_predict_device(osml_knn_index* ix, const int64_t* d_part_idx,
     rc = aggregate(ix, nn_d, nn_i, q, task, d_out_pred, stream);
     if (rc == OSML_KNN_OK) ix->stats.queries += q;
     return rc;
+}
+
+int osml_knn_set_query_transform(osml_knn_index* ix, const void* shift, const void* denom) {
+    if (!ix) return fail(OSML_KNN_EINVAL, "null index");
+    if (!shift) {
+        if (denom) return fail(OSML_KNN_EINVAL, "denom without shift");
+        ix->has_q_transform = ix->has_q_denom = false;
+        return OSML_KNN_OK;
+    }
+    if (ix->dtype != OSML_KNN_F32 && ix->dtype != OSML_KNN_F64)
+        return fail(OSML_KNN_EUNSUPPORTED, "the fused query transform needs a float32 or float64 index");
+    DeviceGuard guard(ix->device);
+    const size_t bytes = (size_t)ix->d * dtype_size(ix->dtype);
+    CUDA_TRY(ix->q_shift.reserve(bytes));
+    CUDA_TRY(cudaMemcpy(ix->q_shift.ptr, shift, bytes, cudaMemcpyHostToDevice));
+    if (denom) {
+        CUDA_TRY(ix->q_denom.reserve(bytes));
+        CUDA_TRY(cudaMemcpy(ix->q_denom.ptr, denom, bytes, cudaMemcpyHostToDevice));
+    }
+    ix->has_q_transform = true;
+    ix->has_q_denom = denom != nullptr;
+    return OSML_KNN_OK;
+}
+
+int osml_knn_column_transform(int device, const void* in, int dtype, int layout, int64_t n, int64_t d,
+                              const void* shift, const void* denom, void* out) {
+    if (!in || !out || !shift) return fail(OSML_KNN_EINVAL, "null argument");
+    if (n < 1 || d < 1) return fail(OSML_KNN_EINVAL, "empty matrix");
+    if (layout != OSML_KNN_ROW_MAJOR && layout != OSML_KNN_COL_MAJOR) return fail(OSML_KNN_EINVAL, "bad layout");
+    const size_t in_es = dtype_size(dtype);
+    if (in_es == 0) return fail(OSML_KNN_EUNSUPPORTED, "unsupported dtype");
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(OSML_KNN_ECUDA, "no such CUDA device");
+    DeviceGuard guard(device);
+    const size_t out_es = dtype == OSML_KNN_F32 ? 4 : 8;
+    const size_t elems = (size_t)n * d;
+    DeviceBuffer d_in, d_out, d_shift, d_denom;
+    auto done = [&](int rc) { d_in.release(); d_out.release(); d_shift.release(); d_denom.release(); return rc; };
+    cudaError_t e;
+    if ((e = d_in.reserve(elems * in_es)) != cudaSuccess || (e = d_out.reserve(elems * out_es)) != cudaSuccess ||
+        (e = d_shift.reserve((size_t)d * out_es)) != cudaSuccess ||
+        (denom && (e = d_denom.reserve((size_t)d * out_es)) != cudaSuccess))
+        return done(fail(e == cudaErrorMemoryAllocation ? OSML_KNN_ENOMEM : OSML_KNN_ECUDA, cudaGetErrorString(e)));
+    if ((e = cudaMemcpy(d_in.ptr, in, elems * in_es, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d_shift.ptr, shift, (size_t)d * out_es, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (denom && (e = cudaMemcpy(d_denom.ptr, denom, (size_t)d * out_es, cudaMemcpyHostToDevice)) != cudaSuccess))
+        return done(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
+    const int cm = layout == OSML_KNN_COL_MAJOR ? 1 : 0;
+    const void* dn = denom ? d_denom.ptr : nullptr;
+    switch (dtype) {
+        case OSML_KNN_F32: e = osml::launch_column_transform<float, float>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
+        case OSML_KNN_F64: e = osml::launch_column_transform<double, double>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
+        case OSML_KNN_I8: e = osml::launch_column_transform<int8_t, double>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
+        case OSML_KNN_I16: e = osml::launch_column_transform<int16_t, double>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
+        case OSML_KNN_I32: e = osml::launch_column_transform<int32_t, double>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
+        case OSML_KNN_I64: e = osml::launch_column_transform<int64_t, double>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
+        case OSML_KNN_U8: e = osml::launch_column_transform<uint8_t, double>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
+        case OSML_KNN_U16: e = osml::launch_column_transform<uint16_t, double>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
+        case OSML_KNN_U32: e = osml::launch_column_transform<uint32_t, double>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
+        default: e = osml::launch_column_transform<uint64_t, double>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
+    }
+    if (e != cudaSuccess) return done(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
+    if ((e = cudaMemcpy(out, d_out.ptr, elems * out_es, cudaMemcpyDeviceToHost)) != cudaSuccess)
+        return done(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
+    return done(OSML_KNN_OK);
 }
 
 int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {

@@ -121,6 +121,7 @@ class KNearestNeighbors(PredictiveModel):
         self.device = None
         self.path = 'auto'
         self._index = None
+        self._query_transform = None     # (shift, denom) fused into predict, see set_query_transform
 
     # -- device state ---------------------------------------------------------------------------------------------
     def _gamma_is_f32(self):
@@ -136,6 +137,8 @@ class KNearestNeighbors(PredictiveModel):
             self._index = _native.Index(self._observations, self._labels, int(self.k), float(self.rbf_gamma),
                                         float(self.epsilon), device=device, gamma_is_f32=self._gamma_is_f32())
             self._index.set_option('path', _native.PATHS[self.path])
+            if getattr(self, '_query_transform', None) is not None:
+                self._index.set_query_transform(*self._query_transform)
         return self._index
 
     def _drop_index(self):
@@ -174,6 +177,20 @@ class KNearestNeighbors(PredictiveModel):
         predictions = np.zeros((len(labels)), )
         predictions[np.asarray(labels)] = positional
         return predictions
+
+    def set_query_transform(self, transform_model):
+        """Not in the reference's API: fuses a fitted ``osml_b200.Centering`` / ``Standardization`` into ``predict``.
+        The model must have been fitted on the TRANSFORMED train frame (as in the reference's pipeline:
+        ``model.fit(std.fit_transform(x, y), y)``); afterwards ``model.predict(raw_query_df)`` equals
+        ``model.predict(std.transform(raw_query_df))`` bit for bit, without the host pass over the query frame.
+        Needs float32 / float64 features of one dtype.  ``None`` removes the transform."""
+        if transform_model is None:
+            self._query_transform = None
+        else:
+            shift, denom = transform_model.shift_and_denominator()
+            self._query_transform = (np.array(shift, copy=True), None if denom is None else np.array(denom, copy=True))
+        if self._index is not None:
+            self._index.set_query_transform(*(self._query_transform or (None, None)))
 
     def kneighbors(self, observations_df):
         """Not in the reference's public API: the (k+1) nearest train indices and distances per query, ascending by

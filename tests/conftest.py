@@ -15,7 +15,29 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz'))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and not f.startswith('transform_'))
+
+
+def transform_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and f.startswith('transform_'))
+
+
+def load_transform_golden(name):
+    """Centering / Standardization fixtures (oracle/make_golden_transform.py); matrices re-laid-out as the reference
+    saw / produced them."""
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+    g = {key: z[key] for key in z.files}
+    for key in ('fit_is_f_order', 'query_is_f_order', 'out_is_f_order', 'epsilon', 'numpy_version', 'pandas_version'):
+        g[key] = g[key][()]
+    order = lambda flag: np.asfortranarray if bool(flag) else np.ascontiguousarray   # noqa: E731
+    g['fit'] = order(g['fit_is_f_order'])(g['fit'])
+    g['query'] = order(g['query_is_f_order'])(g['query'])
+    for key in ('centered_fit', 'centered_query', 'standardized_fit', 'standardized_query'):
+        g[key] = order(g['out_is_f_order'])(g[key])
+    g['epsilon'] = float(g['epsilon'])
+    g['name'] = name
+    return g
 
 
 def load_golden(name):
@@ -40,3 +62,8 @@ def load_golden(name):
 @pytest.fixture(params=golden_names())
 def golden(request):
     return load_golden(request.param)
+
+
+@pytest.fixture(params=transform_golden_names())
+def transform_golden(request):
+    return load_transform_golden(request.param)
