@@ -584,8 +584,22 @@ int osml_knn_column_transform(int device, const void* in, int dtype, int layout,
     DeviceGuard guard(device);
     const size_t out_es = dtype == OSML_KNN_F32 ? 4 : 8;
     const size_t elems = (size_t)n * d;
-    DeviceBuffer d_in, d_out, d_shift, d_denom;
-    auto done = [&](int rc) { d_in.release(); d_out.release(); d_shift.release(); d_denom.release(); return rc; };
+    if (d >= (1 << 24)) return fail(OSML_KNN_EUNSUPPORTED, "too many columns");
+    // device staging buffers are kept per thread between calls (cudaMalloc / cudaFree cost more than the kernel) and
+    // given back when they grow past 1 GB
+    struct Scratch { int device = -1; DeviceBuffer in, out, shift, denom; };
+    static thread_local Scratch sc;
+    if (sc.device != device) {
+        if (sc.device >= 0) { DeviceGuard g2(sc.device); sc.in.release(); sc.out.release(); sc.shift.release(); sc.denom.release(); }
+        sc.device = device;
+    }
+    DeviceBuffer &d_in = sc.in, &d_out = sc.out, &d_shift = sc.shift, &d_denom = sc.denom;
+    auto done = [&](int rc) {
+        if (d_in.cap + d_out.cap > ((size_t)1 << 30) || rc != OSML_KNN_OK) {
+            d_in.release(); d_out.release(); d_shift.release(); d_denom.release();
+        }
+        return rc;
+    };
     cudaError_t e;
     if ((e = d_in.reserve(elems * in_es)) != cudaSuccess || (e = d_out.reserve(elems * out_es)) != cudaSuccess ||
         (e = d_shift.reserve((size_t)d * out_es)) != cudaSuccess ||
