@@ -58,3 +58,22 @@ def test_config3_full_size():
 def test_config5_one_shard_full_size():
     """BASELINE config 5, one GPU's share: 2.5M x 96 fp32 rows, k = 32 (a 20k-query sample of the 1M)."""
     _full_size_case(2_500_000, 96, 20_000, 32, seed=5, sample=128, oracle_sample=3)
+
+
+def test_adversarial_binary_int8_ties_everywhere():
+    """SURVEY.md section 8d's adversarial set: rng.integers(0, 2, (100000, 128)).astype(int8) -- exact distance ties on
+    every query; int8 arithmetic (subtract and square wrap, int64 sum, fp64 sqrt) on the direct kernel, ties resolved
+    by the documented (distance, index) rule."""
+    from tests import parity
+    rng = np.random.default_rng(8)
+    n, d, q, k = 100_000, 128, 120, 10
+    train = np.asfortranarray(rng.integers(0, 2, (n, d)).astype(np.int8))
+    queries = rng.integers(0, 2, (q, d)).astype(np.int8)
+    labels = rng.integers(0, 2, n).astype(np.int8)
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    pred, idx, dist = ix.predict(queries, _native.CLASSIFICATION, return_neighbours=True)
+    ix.close()
+    assert dist.dtype == np.float64
+    assert np.all(np.diff(dist, axis=1) >= 0)
+    assert (np.diff(dist, axis=1) == 0).any(axis=1).all()                 # every query really has ties
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, queries, k, 1, 'classification')
