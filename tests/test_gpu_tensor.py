@@ -189,3 +189,30 @@ def test_rows_with_very_different_norms():
     labels = rng.integers(0, 7, n)
     pred, idx, dist, stats = _run(train, labels, test, k)
     parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+
+
+def test_random_shapes_tensor_path_equals_direct_kernel():
+    """Property test over shapes the fixed cases do not hit: ragged row / query counts, odd feature counts on both
+    sides of the 64-column K blocks, k around the list-length plan boundaries, offset and scaled data.  The filter path
+    must be bit-identical to the exact direct kernel whatever it keeps or drops."""
+    rng = np.random.default_rng(2024)
+    for case in range(24):
+        n = int(rng.integers(300, 40000))
+        d = int(rng.choice([1, 2, 5, 16, 31, 63, 64, 65, 100, 127, 128, 129, 191, 193, 253, 254, 300]))
+        q = int(rng.integers(1, 900))
+        k = int(rng.choice([1, 2, 5, 7, 10, 13, 14, 21, 22, 32, 40]))
+        if n < k + 2:
+            continue
+        scale = float(np.exp(rng.uniform(-3, 3)))
+        train = np.asfortranarray((rng.standard_normal((n, d)) * scale + rng.uniform(-5, 5, d)).astype(np.float32))
+        test = (rng.standard_normal((q, d)) * scale + rng.uniform(-5, 5, d)).astype(np.float32)
+        labels = rng.standard_normal(n)
+        pred, idx, dist, stats = _run(train, labels, test, k, task='regression')
+        ix = _native.Index(train, labels, k, 1, 1e-8)
+        ix.set_option('path', _native.PATH_DIRECT)
+        d_pred, d_idx, d_dist = ix.predict(test, _native.REGRESSION, return_neighbours=True)
+        ix.close()
+        where = 'case %d: n=%d d=%d q=%d k=%d' % (case, n, d, q, k)
+        assert np.array_equal(idx, d_idx), where
+        assert np.array_equal(dist, d_dist), where
+        assert np.array_equal(pred, d_pred), where
