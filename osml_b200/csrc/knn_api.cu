@@ -96,6 +96,7 @@ struct osml_knn_index {
     int opt_nseg = 0;
     int opt_smem_lists = 0;
     int opt_cta_group = 0;
+    int opt_active = 0;
     int debug = 0;
     int counters = 0;
     int64_t query_block = 0;
@@ -285,7 +286,7 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         tl.train = ix->train.ptr; tl.dtype = ix->dtype; tl.n = ix->n; tl.d = ix->d; tl.k = ix->k;
         tl.sum_order = ix->sum_order; tl.index_base = ix->index_base; tl.slack = ix->slack;
         tl.opt_epi_warps = ix->opt_epi_warps; tl.opt_nseg = ix->opt_nseg; tl.debug = ix->debug; tl.counters = ix->counters;
-        tl.opt_smem_lists = ix->opt_smem_lists; tl.opt_cta_group = ix->opt_cta_group;
+        tl.opt_smem_lists = ix->opt_smem_lists; tl.opt_cta_group = ix->opt_cta_group; tl.opt_active = ix->opt_active;
         int64_t fallback = 0, launches = 0;
         std::string err;
         int rc = osml::tensor_neighbours(ix->tensor, tl, d_queries, q, out_d, out_i, stream, &fallback, &launches, &err,
@@ -647,6 +648,7 @@ int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
     if (key == "counters") { ix->counters = (int)value; return OSML_KNN_OK; }
     if (key == "smem_lists") { ix->opt_smem_lists = (int)value; return OSML_KNN_OK; }
     if (key == "cta_group") { ix->opt_cta_group = (int)value; return OSML_KNN_OK; }
+    if (key == "active") { ix->opt_active = (int)value; return OSML_KNN_OK; }
     if (key == "query_block") { ix->query_block = (int64_t)value; return OSML_KNN_OK; }
     return fail(OSML_KNN_EINVAL, "unknown option: " + key);
 }

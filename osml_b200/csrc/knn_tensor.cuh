@@ -69,6 +69,7 @@ struct TcParams {
                          // whole range of row norms, in ascending order)
     int tiles_total;
     int kprime;          // candidates kept per (query, slot)
+    int kactive;         // pair kernel: list entries in use, <= kprime (see TcRegList::reset)
     int epi_warps;       // 4 or 8
     int stages;          // B ring depth
     int a_resident;      // 1: the query tile stays in shared memory for a whole sweep; 0 (wide rows): its K blocks
@@ -329,11 +330,13 @@ struct TcRegList {
         buf_addr = addr; buf_stride = stride; buf_shift = 31 - __clz((int)stride); cnt = 0; rd = 0;
     }
     // empty slots hold -FLT_MAX, or a seed threshold proven elsewhere (values at or below it are never inserted)
-    __device__ __forceinline__ void reset(float seed = -INFINITY) {
+    // `active` <= KP entries take part; the others are parked at +FLT_MAX so that they are never the minimum (a list
+    // length between the powers of two the slot packing allows: fewer entries -> higher threshold -> fewer hits)
+    __device__ __forceinline__ void reset(float seed = -INFINITY, int active = KP) {
         const uint32_t base = seed > -3.0e38f ? __float_as_uint(seed) : 0xFF7FFFFFu;
 #pragma unroll
         for (int e = 0; e < KP; ++e) {
-            lv[e] = __uint_as_float((base & ~kSlotMask) | (uint32_t)e);
+            lv[e] = __uint_as_float((((e < active) ? base : 0x7F7FFFFFu) & ~kSlotMask) | (uint32_t)e);
             if (kSmemRows) sts_b32(rows_addr + (uint32_t)e * rows_stride, 0xffffffffu);
             else lr[e] = -1;
         }
@@ -954,7 +957,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 float seed = -INFINITY;
                 for (int s2 = 0; s2 < seg; ++s2)
                     seed = fmaxf(seed, *(const volatile float*)(p.cand_thr + q * p.nslot + (size_t)s2 * halves + half));
-                list.reset(seed);
+                list.reset(seed, p.kactive);
                 if (p.debug == 4) list.thr = INFINITY;       // ablation: fast path only
                 int row_base = tile0 * kTcBN + half * cols;
                 for (int t = 0; t < ntiles; ++t, ++acc_it, row_base += nsg * kTcBN) {
@@ -1052,11 +1055,11 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 const size_t slot = (size_t)seg * halves + half;
                 float* ov = p.cand_val + (q * p.nslot + slot) * KP;
                 int* oi = p.cand_idx + (q * p.nslot + slot) * KP;
-                bool full = true;
+                int filled = 0;
     #pragma unroll
-                for (int e = 0; e < KP; ++e) { const int r = list.row_of(e); ov[e] = list.lv[e]; oi[e] = r; full = full && r >= 0; }
+                for (int e = 0; e < KP; ++e) { const int r = list.row_of(e); ov[e] = list.lv[e]; oi[e] = r; filled += r >= 0 ? 1 : 0; }
                 // everything this slot dropped scores <= thr (placeholders keep thr at the seed while the list is not full)
-                p.cand_thr[q * p.nslot + slot] = (full || seed > -INFINITY) ? list.thr : -INFINITY;
+                p.cand_thr[q * p.nslot + slot] = (filled >= p.kactive || seed > -INFINITY) ? list.thr : -INFINITY;
             }
             if ((OSML_TC_COUNTERS && p.counters) && lane == 0) {
                 atomicAdd(p.dbg + 3, (unsigned long long)dbg_epi_wait);
@@ -1320,6 +1323,7 @@ struct TensorLaunch {
     int opt_nseg = 0;        // 0 = auto
     int opt_smem_lists = 0;  // 1 = force the shared-memory list epilogue
     int opt_cta_group = 0;   // 0 = auto, 1 = single CTA per item, 2 = CTA pairs (cta_group::2)
+    int opt_active = 0;      // 0 = auto (= K'), else list entries in use per slot (experiments)
     int debug = 0;
     int counters = 0;        // 1 = the CTA-pair kernel records where its issuer / epilogue warps wait (printed to stderr)
 };
@@ -1560,7 +1564,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
 
     TcParams p;
     p.nkb = nkb; p.ksteps = ksteps; p.nqt = nqt; p.nseg = nseg; p.nq_single = nq_single; p.tiles_per_seg = tiles_per_seg;
-    p.tiles_total = tiles_total; p.kprime = kprime; p.epi_warps = epi_warps; p.stages = stages; p.nslot = nslot; p.a_resident = a_resident ? 1 : 0;
+    p.tiles_total = tiles_total; p.kprime = kprime; p.kactive = (tl.opt_active > 0 && tl.opt_active <= kprime) ? tl.opt_active : kprime; p.epi_warps = epi_warps; p.stages = stages; p.nslot = nslot; p.a_resident = a_resident ? 1 : 0;
     p.cand_val = sc.cand_val.as<float>(); p.cand_idx = sc.cand_idx.as<int>();
     p.cand_thr = sc.cand_thr.as<float>();
     p.h = st.half_norm.as<float>(); p.hmin8 = st.hmin8.as<float>(); p.hblk = st.hblk.as<float>();
