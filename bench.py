@@ -101,6 +101,14 @@ def run_reference_arm(args):
         return 0
     train, labels, queries, k = make_data(args.workload, 0)
     cores = len(os.sched_getaffinity(0))
+    # every worker holds two N x D temporaries per query (predict.py:742): bound the pool by the memory that is there
+    per_worker_bytes = 3 * train.nbytes
+    try:
+        import psutil
+        by_memory = int(psutil.virtual_memory().available * 0.5 // per_worker_bytes)
+    except Exception:
+        by_memory = 16
+    cores = max(1, min(cores, by_memory, 64))
     _cpu_init(train, labels, k)
     t0 = time.perf_counter()
     _cpu_predict(queries[:1])
