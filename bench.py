@@ -110,14 +110,16 @@ def run_reference_arm(args):
         by_memory = 16
     cores = max(1, min(cores, by_memory, 64))
     _cpu_init(train, labels, k)
-    t0 = time.perf_counter()
-    _cpu_predict(queries[:1])
-    per_query = time.perf_counter() - t0
-    # bounded sample per step: about 4 s of wall clock per step with every core busy
-    per_worker = int(max(1, min(16, 4.0 / max(per_query, 1e-6))))
-    sample = per_worker * cores
     ctx = mp.get_context('fork')
     with ctx.Pool(cores) as pool:
+        # bounded sample per step: about 4 s of wall clock per step with every worker busy (calibrated under load:
+        # the numpy path is DRAM-bound, so a query takes longer when all cores stream at once)
+        pool.map(_cpu_predict, [queries[i:i + 1] for i in range(cores)])
+        t0 = time.perf_counter()
+        pool.map(_cpu_predict, [queries[i:i + 1] for i in range(cores)])
+        per_query = time.perf_counter() - t0
+        per_worker = int(max(1, min(16, 4.0 / max(per_query, 1e-6))))
+        sample = per_worker * cores
         chunks = [queries[i * per_worker:(i + 1) * per_worker] for i in range(cores)]
         for _ in range(args.warmup):
             pool.map(_cpu_predict, chunks)
