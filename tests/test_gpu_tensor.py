@@ -216,3 +216,19 @@ def test_random_shapes_tensor_path_equals_direct_kernel():
         assert np.array_equal(idx, d_idx), where
         assert np.array_equal(dist, d_dist), where
         assert np.array_equal(pred, d_pred), where
+
+
+def test_more_queries_than_one_block():
+    """The filter processes queries in blocks of 131072: two blocks, the second one ragged."""
+    rng = np.random.default_rng(31)
+    n, d, q, k = 30000, 16, 131072 + 8929, 5
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = rng.standard_normal((q, d), dtype=np.float32)
+    labels = rng.integers(0, 6, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    ix.set_option('path', _native.PATH_DIRECT)
+    d_pred, d_idx, d_dist = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    ix.close()
+    assert np.array_equal(idx, d_idx) and np.array_equal(dist, d_dist) and np.array_equal(pred, d_pred)
+    assert stats['tensor_queries'] == q

@@ -8,7 +8,7 @@
 using namespace osml;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
-pair_rate_kernel(int ksteps, int tiles, int commit_every, int mode, long long* cycles) {
+pair_rate_kernel(int ksteps, int tiles, int commit_every, int mode, int n_cols, long long* cycles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar, bar2, bar3, done;
     __shared__ uint32_t slot;
@@ -26,7 +26,7 @@ pair_rate_kernel(int ksteps, int tiles, int commit_every, int mode, long long* c
     ptx::tc_fence_before(); ptx::cluster_sync_all(); ptx::tc_fence_after();
     const uint32_t tmem = slot;
     if (warp == 1 && lane == 0 && rank == 0) {
-        const uint32_t idesc = ptx::umma_idesc_bf16(256, 256);
+        const uint32_t idesc = ptx::umma_idesc_bf16(256, n_cols);
         const uint32_t hi = ptx::umma_desc_hi_k_sw128();
         const uint32_t a_lo0 = ptx::umma_desc_lo(ptx::smem_u32(smem)), b_lo0 = ptx::umma_desc_lo(ptx::smem_u32(smem) + 16384 * 2);
         long long t0 = clock64();
@@ -60,14 +60,14 @@ int main() {
     long long* d_c; cudaMalloc(&d_c, 74 * 8);
     const size_t smem = 16384 * 2 + 32768 * 5 + 1024;
     cudaFuncSetAttribute(pair_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int mode : {0, 4, 5})
+    for (int n_cols : {256, 128, 64})
         for (int ks : {6, 8}) {
-            const int grid = 148, tiles = 400000, commit_every = 1;
-            pair_rate_kernel<<<grid, 384, smem>>>(ks, tiles, commit_every, mode, d_c);
+            const int grid = 148, tiles = 40000, commit_every = 1, mode = 4;
+            pair_rate_kernel<<<grid, 384, smem>>>(ks, tiles, commit_every, mode, n_cols, d_c);
             cudaError_t e = cudaDeviceSynchronize();
             long long c[74]; cudaMemcpy(c, d_c, 74 * 8, cudaMemcpyDeviceToHost);
             long long mx = 0; for (int i = 0; i < grid / 2; ++i) mx = c[i] > mx ? c[i] : mx;
-            printf("mode=%d (bit0: B ring, bit1: polling warps, bit2: random operand bits) commit_every=%d grid=%3d ksteps=%2d: %.1f cycles/tile, %.1f cycles/MMA (%s)\n", mode, commit_every, grid, ks, (double)mx / tiles,
+            printf("N=%d mode=%d commit_every=%d grid=%3d ksteps=%2d: %.1f cycles/tile, %.1f cycles/MMA (%s)\n", n_cols, mode, commit_every, grid, ks, (double)mx / tiles,
                    (double)mx / tiles / ks, cudaGetErrorString(e));
         }
     return 0;
