@@ -777,8 +777,8 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     const int epi_threads = p.epi_warps * 32;
     unsigned char* cand_buf = b_smem + (size_t)p.stages * stage_bytes;         // [kTcBufCap][epi_threads] x 8 B
     unsigned char* h_ring = cand_buf + (size_t)kTcBufCap * epi_threads * 8;     // [kTcHSlots][kTcHBlock] floats
-    unsigned char* row_lists = h_ring + (size_t)kTcHSlots * kTcHBlock * 4;     // K' > 16: [K'][epi_threads] ints
-    uint64_t* bars = reinterpret_cast<uint64_t*>(row_lists + (KP > 16 ? (size_t)KP * epi_threads * 4 : 0));
+    unsigned char* row_lists = h_ring + (size_t)kTcHSlots * kTcHBlock * 4;     // [K'][epi_threads] ints
+    uint64_t* bars = reinterpret_cast<uint64_t*>(row_lists + (size_t)KP * epi_threads * 4);
     uint64_t* full_bar = bars;                    // [stages]  (used in the leader)
     uint64_t* empty_bar = bars + 8;               // [stages]
     uint64_t* tmem_full = bars + 16;              // [2]
@@ -930,7 +930,9 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const int cols = kTcBN / halves;
             const int m = quarter * 32 + lane;
             uint32_t acc_it = 0, hslot = 0, hphase = 0;
-            constexpr bool kSmemRows = KP > 16;
+            // row indices of the list entries live in shared memory: an insert touches K' value registers only (2
+            // instead of 3 instructions per entry: -2 % kernel cycles at K' = 16) and K' = 32 fits next to the staged tile
+            constexpr bool kSmemRows = true;
             TcRegList<KP, kSmemRows> list;
             list.rows_addr = ptx::smem_u32(row_lists) + (uint32_t)(ew * 32 + lane) * 4u;
             list.rows_stride = (uint32_t)epi_threads * 4u;
@@ -1490,8 +1492,8 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     // CTA pairs (cta_group::2) need register lists (no shared-memory list code in that kernel)
     // (the pair kernel stages whole half-tiles; for wide rows that no longer fits twice, so use single CTAs there)
     const size_t pair_stage = (size_t)(st.dp / kTcKB) * kTcBHalfBytes;
-    // pair kernel only: h ring + its barriers, and the lists' row indices when K' = 32
-    const size_t pair_extra = (size_t)kTcHSlots * kTcHBlock * 4 + 256 + (kprime > 16 ? (size_t)kprime * epi_warps * 32 * 4 : 0);
+    // pair kernel only: h ring + its barriers, and the lists' row indices
+    const size_t pair_extra = (size_t)kTcHSlots * kTcHBlock * 4 + 256 + (size_t)kprime * epi_warps * 32 * 4;
     const bool pair_fits = (size_t)st.smem_optin >=
         (size_t)(st.dp / kTcKB) * kTcABlockBytes + 2 * pair_stage + (size_t)kTcBufCap * 8 * 32 * 8 + pair_extra + 1280;
     const int tc_cta_group = (reg_lists && tl.opt_cta_group != 1 && pair_fits) ? 2 : 1;
