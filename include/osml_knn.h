@@ -75,6 +75,9 @@ typedef struct osml_knn_stats {
     int64_t device_bytes;        /* device memory held by the handle */
     int64_t retry_queries;       /* queries K3 could not prove on the first filter pass and that went through the
                                     finer-grained second filter pass (those it still cannot prove count as fallback) */
+    int64_t filter_precision;    /* element type of the tensor filter copy in use: 0 not built yet, 1 bf16, 2 fp16 (option
+                                    "precision": 0 auto -- bf16, fp16 once a call sent > 0.25 % of its queries to the
+                                    second pass --, 1 bf16, 2 fp16) */
 } osml_knn_stats;
 
 /*

@@ -37,7 +37,7 @@ class Stats(ctypes.Structure):
                 ('fallback_queries', ctypes.c_int64), ('tensor_queries', ctypes.c_int64),
                 ('last_filter_ms', ctypes.c_double), ('last_total_ms', ctypes.c_double),
                 ('last_filter_launches', ctypes.c_int64), ('device_bytes', ctypes.c_int64),
-                ('retry_queries', ctypes.c_int64)]
+                ('retry_queries', ctypes.c_int64), ('filter_precision', ctypes.c_int64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -97,6 +97,7 @@ struct osml_knn_index {
     int opt_smem_lists = 0;
     int opt_cta_group = 0;
     int opt_active = 0;
+    int opt_precision = 0;
     int debug = 0;
     int counters = 0;
     int64_t query_block = 0;
@@ -286,7 +287,7 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         tl.train = ix->train.ptr; tl.dtype = ix->dtype; tl.n = ix->n; tl.d = ix->d; tl.k = ix->k;
         tl.sum_order = ix->sum_order; tl.index_base = ix->index_base; tl.slack = ix->slack;
         tl.opt_epi_warps = ix->opt_epi_warps; tl.opt_nseg = ix->opt_nseg; tl.debug = ix->debug; tl.counters = ix->counters;
-        tl.opt_smem_lists = ix->opt_smem_lists; tl.opt_cta_group = ix->opt_cta_group; tl.opt_active = ix->opt_active;
+        tl.opt_smem_lists = ix->opt_smem_lists; tl.opt_cta_group = ix->opt_cta_group; tl.opt_active = ix->opt_active; tl.opt_precision = ix->opt_precision;
         int64_t fallback = 0, launches = 0;
         std::string err;
         int rc = osml::tensor_neighbours(ix->tensor, tl, d_queries, q, out_d, out_i, stream, &fallback, &launches, &err,
@@ -337,7 +338,7 @@ int check_predict_args(const osml_knn_index* ix, int64_t q) {
 
 extern "C" {
 
-int osml_knn_abi_version(void) { return 1002; }
+int osml_knn_abi_version(void) { return 1003; }
 
 const char* osml_knn_last_error(void) { return g_last_error.c_str(); }
 
@@ -649,6 +650,12 @@ int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
     if (key == "smem_lists") { ix->opt_smem_lists = (int)value; return OSML_KNN_OK; }
     if (key == "cta_group") { ix->opt_cta_group = (int)value; return OSML_KNN_OK; }
     if (key == "active") { ix->opt_active = (int)value; return OSML_KNN_OK; }
+    if (key == "precision") {           // 0 = auto, 1 = bf16 filter copy, 2 = fp16 filter copy
+        const int v = (int)value;
+        if (v < 0 || v > 2) return fail(OSML_KNN_EINVAL, "bad precision");
+        ix->opt_precision = v;
+        return OSML_KNN_OK;
+    }
     if (key == "query_block") { ix->query_block = (int64_t)value; return OSML_KNN_OK; }
     return fail(OSML_KNN_EINVAL, "unknown option: " + key);
 }
@@ -658,6 +665,7 @@ int osml_knn_get_stats(osml_knn_index* ix, osml_knn_stats* out) {
     ix->stats.device_bytes = (int64_t)(ix->train.cap + ix->label_bits.cap + ix->stage.cap + ix->queries.cap +
                                        ix->part_d.cap + ix->part_i.cap + ix->nn_d.cap + ix->nn_i.cap + ix->pred.cap +
                                        osml::tensor_bytes(ix->tensor));
+    ix->stats.filter_precision = ix->tensor.ready ? (ix->tensor.f16 ? 2 : 1) : 0;
     *out = ix->stats;
     return OSML_KNN_OK;
 }

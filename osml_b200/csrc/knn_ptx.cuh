@@ -143,6 +143,10 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// the same with FP16 operands (a_format = b_format = 0): same rate, three more significand bits
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by one thread
 __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,

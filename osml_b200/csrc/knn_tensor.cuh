@@ -27,6 +27,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -69,6 +70,7 @@ struct TcParams {
                          // whole range of row norms, in ascending order)
     int tiles_total;
     int kprime;          // candidates kept per (query, slot)
+    int f16;             // operands are fp16 (else bf16)
     int kactive;         // pair kernel: list entries in use, <= kprime (see TcRegList::reset)
     int epi_warps;       // 4 or 8
     int stages;          // B ring depth
@@ -126,10 +128,43 @@ struct TcPrepStats {          // device-side reductions over the train rows
     int nonfinite;
 };
 
-// Pass A over the train rows (one warp per row): h = 0.5*|t^|^2 of the centred, bf16-rounded row, the rounding residual
+// Element type of the filter copies (TensorState::f16).  bf16: the default.  fp16 of the centred values times a
+// power-of-two scale: 11 significand bits, so rounding residuals 8x smaller and the completeness proof has 8x more
+// room -- the choice when many queries need the second filter pass (it costs ~3 % more K1 time through the power
+// cap, measured at the same cycle count, so it only pays when it saves retries).  Both are 16-bit: tc_elem is raw bits.
+using tc_elem = unsigned short;
+template <bool kF16>
+__device__ __forceinline__ tc_elem tc_round(float x) {
+    if (kF16) {     // subnormal results are flushed to zero so that the tensor core sees exactly what the residuals assume
+        const __half h = __float2half_rn(x);
+        return fabsf(__half2float(h)) < 6.103515625e-05f ? (tc_elem)0 : __half_as_ushort(h);
+    }
+    return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+template <bool kF16>
+__device__ __forceinline__ float tc_value(tc_elem h) {
+    return kF16 ? __half2float(__ushort_as_half(h)) : __bfloat162float(__ushort_as_bfloat16(h));
+}
+
+// max |t - c| over the train set (finite values only): fixes the power-of-two scale of the fp16 filter copy
+__global__ void tc_max_abs_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ center,
+                                  unsigned int* __restrict__ max_bits) {
+    const int64_t total = n * d;
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = fabsf(__fsub_rn(x[i], center[i % d]));
+        if (a < INFINITY) m = fmaxf(m, a);
+    }
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_bits, __float_as_uint(m));
+}
+
+// Pass A over the train rows (one warp per row): h = 0.5*|t^|^2 of the centred, rounded row, the rounding residual
 // |t^ - (t - c)| and the maxima the completeness bound needs.  h is the sort key of the filter copy.
+template <bool kF16>
 __global__ void tc_train_norms_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ center,
-                                      float* __restrict__ half_norm, int* __restrict__ iota, TcPrepStats* stats) {
+                                      float scale, float* __restrict__ half_norm, int* __restrict__ iota,
+                                      TcPrepStats* stats) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;
@@ -137,8 +172,8 @@ __global__ void tc_train_norms_kernel(const float* __restrict__ x, int64_t n, in
     double n2 = 0.0, e2 = 0.0;
     for (int j = lane; j < d; j += 32) {
         const float v = xr[j], c = center[j];
-        const double hd = (double)__bfloat162float(__float2bfloat16_rn(__fsub_rn(v, c)));
-        const double diff = hd - ((double)v - (double)c);
+        const double hd = (double)tc_value<kF16>(tc_round<kF16>(__fmul_rn(__fsub_rn(v, c), scale)));
+        const double diff = hd - ((double)v - (double)c) * (double)scale;
         n2 += hd * hd;
         e2 += diff * diff;
     }
@@ -161,18 +196,18 @@ __global__ void tc_train_norms_kernel(const float* __restrict__ x, int64_t n, in
 // rows nearest to the centre -- the likeliest neighbours of any query -- are scanned first and the per-query
 // thresholds settle early; groups of 8 consecutive rows also get nearly equal h, which keeps the group test tight).
 // Queries (kTrain == false) keep their order and also record |q^|^2 and |q^ - (q - c)|.
-template <bool kTrain>
+template <bool kTrain, bool kF16>
 __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t npad, int d, int dp,
-                                    const float* __restrict__ center, const int* __restrict__ perm,
-                                    __nv_bfloat16* __restrict__ out, double* __restrict__ norm2,
+                                    const float* __restrict__ center, float scale, const int* __restrict__ perm,
+                                    tc_elem* __restrict__ out, double* __restrict__ norm2,
                                     double* __restrict__ err, float* __restrict__ half_norm_sorted,
                                     int* __restrict__ perm_pad) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= npad) return;
-    __nv_bfloat16* o = out + row * dp;
+    tc_elem* o = out + row * dp;
     if (row >= n) {                       // padding row: can never be selected (train) / is ignored (queries)
-        for (int j = lane; j < dp; j += 32) o[j] = __float2bfloat16(0.0f);
+        for (int j = lane; j < dp; j += 32) o[j] = 0;
         if (kTrain && lane == 0) { half_norm_sorted[row] = INFINITY; perm_pad[row] = -1; }
         if (!kTrain && lane == 0 && norm2) { norm2[row] = 0.0; err[row] = 0.0; }
         return;
@@ -181,16 +216,16 @@ __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int6
     double n2 = 0.0, e2 = 0.0;
     for (int j = lane; j < d; j += 32) {
         const float v = xr[j], c = center[j];
-        const __nv_bfloat16 h = __float2bfloat16_rn(__fsub_rn(v, c));
+        const tc_elem h = tc_round<kF16>(__fmul_rn(__fsub_rn(v, c), scale));
         o[j] = h;
         if (!kTrain) {
-            const double hd = (double)__bfloat162float(h);
-            const double diff = hd - ((double)v - (double)c);
+            const double hd = (double)tc_value<kF16>(h);
+            const double diff = hd - ((double)v - (double)c) * (double)scale;
             n2 += hd * hd;
             e2 += diff * diff;
         }
     }
-    for (int j = d + lane; j < dp; j += 32) o[j] = __float2bfloat16(0.0f);
+    for (int j = d + lane; j < dp; j += 32) o[j] = 0;
     if (!kTrain) {
         for (int off = 16; off > 0; off >>= 1) {
             n2 += __shfl_xor_sync(0xffffffffu, n2, off);
@@ -569,7 +604,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            const uint32_t idesc = ptx::umma_idesc_bf16(kTcBM, kTcBN);
+            const uint32_t idesc = (p.f16 ? ptx::umma_idesc_f16(kTcBM, kTcBN) : ptx::umma_idesc_bf16(kTcBM, kTcBN));
             const uint32_t hi = ptx::umma_desc_hi_k_sw128();
             const uint32_t a_lo0 = ptx::umma_desc_lo(ptx::smem_u32(a_smem)), b_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_smem));
             uint32_t stage = 0, phase = 0, it = 0, acc_it = 0;
@@ -863,7 +898,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 // thread waits and commits while the other keeps the pipe fed.  Tiles of different parity write
                 // different TMEM stages and read different shared-memory stages, so their relative order is free.
                 const uint32_t issuer = (uint32_t)warp >> 1;
-                const uint32_t idesc = ptx::umma_idesc_bf16(2 * kTcBM, kTcBN);
+                const uint32_t idesc = (p.f16 ? ptx::umma_idesc_f16(2 * kTcBM, kTcBN) : ptx::umma_idesc_bf16(2 * kTcBM, kTcBN));
                 const uint32_t hi = ptx::umma_desc_hi_k_sw128();
                 const uint32_t a_lo0 = ptx::umma_desc_lo(ptx::smem_u32(a_smem)), b_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_smem));
                 uint32_t stage = 0, phase = 0, it = 0, acc_it = 0;
@@ -1093,6 +1128,7 @@ struct TcBounds {
     double tnorm_max;     // max |t^|
     double c_mma;         // relative accumulation error of the tensor core sum, per unit of sum |terms|
     double gamma;         // relative error of the oracle's fp32 distance
+    double inv_scale;     // 1 / scale of the filter copy: scores, norms and residuals above are in scaled units
 };
 
 constexpr int kRescoreWarps = 4;
@@ -1160,7 +1196,7 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
     // every row whose filter score is <= a has an exact (oracle-arithmetic) distance >= lower(a)
     auto lower = [&](float a) {
         const double l2 = n2 - 2.0 * ((double)a + eps);
-        return (sqrt(fmax(l2, 0.0)) - (eq + bounds.et_max)) * (1.0 - bounds.gamma);
+        return (sqrt(fmax(l2, 0.0)) - (eq + bounds.et_max)) * bounds.inv_scale * (1.0 - bounds.gamma);
     };
 
     int nvalid = 0;
@@ -1291,7 +1327,10 @@ struct TensorState {
     bool ready = false;
     bool usable = false;          // false if the train set has non-finite rows (then only K2 is exact)
     int64_t npad = 0; int dp = 0;
-    double et_max = 0.0, tnorm_max = 0.0;
+    double et_max = 0.0, tnorm_max = 0.0;   // in units of the scaled filter copy
+    float scale = 1.0f;                     // power of two applied to t - c and q - c before rounding
+    bool f16 = false;                       // element type of the filter copies (see tc_round)
+    bool want_f16 = false;                  // set when a call needed too many second passes: rebuild in fp16 next time
     TcBuffer train_bf16, half_norm, hmin8, hblk, perm, center, stats, partial;
     TcBuffer dbg;
     // per-call scratch; level 0 = the caller's queries, level 1 = the retry of the few queries K3 could not prove
@@ -1326,6 +1365,7 @@ struct TensorLaunch {
     int opt_smem_lists = 0;  // 1 = force the shared-memory list epilogue
     int opt_cta_group = 0;   // 0 = auto, 1 = single CTA per item, 2 = CTA pairs (cta_group::2)
     int opt_active = 0;      // 0 = auto (= K'), else list entries in use per slot (experiments)
+    int opt_precision = 0;   // 0 = auto (bf16, fp16 once a call needed many second passes), 1 = bf16, 2 = fp16
     int debug = 0;
     int counters = 0;        // 1 = the CTA-pair kernel records where its issuer / epilogue warps wait (printed to stderr)
 };
@@ -1380,7 +1420,7 @@ inline int tc_make_map(TensorState& st, CUtensorMap* map, void* base, int64_t ro
     const cuuint32_t box[2] = {(cuuint32_t)kTcKB, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = reinterpret_cast<TcEncodeTiledFn>(st.encode_fn)(
-        map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        map, st.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
@@ -1402,7 +1442,10 @@ inline int tc_make_map(TensorState& st, CUtensorMap* map, void* base, int64_t ro
 // one-time K0 over the train set
 inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stream, int64_t* launches,
                       std::string* err) {
-    if (st.ready) return 0;
+    const bool f16 = tl.opt_precision == 2 || (tl.opt_precision == 0 && st.want_f16);
+    if (st.ready && st.f16 == f16) return 0;
+    st.ready = false;                    // first build, or a rebuild of the filter copy in the other element type
+    st.f16 = f16;
     int dev = 0;
     TC_TRY(cudaGetDevice(&dev));
     TC_TRY(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -1421,9 +1464,9 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
     const int nblocks = (int)((tl.n + rows_per_block - 1) / rows_per_block);
     TC_TRY(st.partial.reserve((size_t)nblocks * d * sizeof(double)));
     TC_TRY(st.center.reserve((size_t)d * sizeof(float)));
-    TC_TRY(st.stats.reserve(sizeof(TcPrepStats)));
-    TC_TRY(st.train_bf16.reserve((size_t)st.npad * st.dp * sizeof(__nv_bfloat16)));
-    TC_TRY(cudaMemsetAsync(st.stats.ptr, 0, sizeof(TcPrepStats), stream));
+    TC_TRY(st.stats.reserve(sizeof(TcPrepStats) + 16));
+    TC_TRY(st.train_bf16.reserve((size_t)st.npad * st.dp * sizeof(tc_elem)));
+    TC_TRY(cudaMemsetAsync(st.stats.ptr, 0, sizeof(TcPrepStats) + 16, stream));
     tc_col_partial_sums_kernel<<<nblocks, dim3(32, 8), 0, stream>>>(train, tl.n, d, rows_per_block,
                                                                     st.partial.as<double>());
     tc_col_mean_kernel<<<(d + 127) / 128, 128, 0, stream>>>(st.partial.as<double>(), nblocks, d, tl.n,
@@ -1437,8 +1480,27 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
         TcBuffer keys_in, vals_in, temp;
         TC_TRY(keys_in.reserve((size_t)tl.n * sizeof(float)));
         TC_TRY(vals_in.reserve((size_t)tl.n * sizeof(int)));
-        tc_train_norms_kernel<<<(unsigned)((tl.n * 32 + 255) / 256), 256, 0, stream>>>(
-            train, tl.n, d, st.center.as<float>(), keys_in.as<float>(), vals_in.as<int>(), st.stats.as<TcPrepStats>());
+        st.scale = 1.0f;
+        if (st.f16) {
+            // power-of-two scale that puts max |t - c| near 2^14: fp16 keeps 11 significant bits down to 2^-14, and
+            // queries up to 4x farther out than any train row still fit (beyond that they fall back through K3)
+            unsigned int* max_bits = reinterpret_cast<unsigned int*>(st.stats.as<unsigned char>() + sizeof(TcPrepStats));
+            tc_max_abs_kernel<<<148 * 8, 256, 0, stream>>>(train, tl.n, d, st.center.as<float>(), max_bits);
+            unsigned int hbits = 0;
+            TC_TRY(cudaMemcpyAsync(&hbits, max_bits, sizeof(hbits), cudaMemcpyDeviceToHost, stream));
+            TC_TRY(cudaStreamSynchronize(stream));
+            float max_abs;
+            memcpy(&max_abs, &hbits, 4);
+            if (max_abs > 0.0f && max_abs < INFINITY) {
+                int e = 0;
+                std::frexp(max_abs, &e);                          // max_abs = m * 2^e, m in [0.5, 1)
+                st.scale = std::ldexp(1.0f, std::max(-100, std::min(100, 14 - e)));
+            }
+            ++*launches;
+        }
+        (st.f16 ? tc_train_norms_kernel<true> : tc_train_norms_kernel<false>)<<<(unsigned)((tl.n * 32 + 255) / 256), 256, 0, stream>>>(
+            train, tl.n, d, st.center.as<float>(), st.scale, keys_in.as<float>(), vals_in.as<int>(),
+            st.stats.as<TcPrepStats>());
         size_t temp_bytes = 0;
         TC_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in.as<float>(), st.half_norm.as<float>(),
                                                vals_in.as<int>(), st.perm.as<int>(), (int)tl.n, 0, 32, stream));
@@ -1446,9 +1508,9 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
         TC_TRY(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, keys_in.as<float>(), st.half_norm.as<float>(),
                                                vals_in.as<int>(), st.perm.as<int>(), (int)tl.n, 0, 32, stream));
         const int64_t threads = st.npad * 32;
-        tc_prep_rows_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
-            train, tl.n, st.npad, d, st.dp, st.center.as<float>(), st.perm.as<int>(), st.train_bf16.as<__nv_bfloat16>(),
-            nullptr, nullptr, st.half_norm.as<float>(), st.perm.as<int>());
+        (st.f16 ? tc_prep_rows_kernel<true, true> : tc_prep_rows_kernel<true, false>)<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+            train, tl.n, st.npad, d, st.dp, st.center.as<float>(), st.scale, st.perm.as<int>(),
+            st.train_bf16.as<tc_elem>(), nullptr, nullptr, st.half_norm.as<float>(), st.perm.as<int>());
         tc_hblock_kernel<<<(unsigned)((st.npad / 8 + 255) / 256), 256, 0, stream>>>(
             st.half_norm.as<float>(), st.npad, st.hmin8.as<float>(), st.hblk.as<float>());
         *launches += 6;
@@ -1543,7 +1605,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     if (stages < 2) { if (err) *err = "not enough shared memory for the tensor filter"; return 4; }
     const size_t smem = a_bytes + (size_t)stages * stage_bytes + list_bytes + extra + 256;
 
-    TC_TRY(sc.q_bf16.reserve((size_t)qpad * st.dp * sizeof(__nv_bfloat16)));
+    TC_TRY(sc.q_bf16.reserve((size_t)qpad * st.dp * sizeof(tc_elem)));
     TC_TRY(sc.q_norm2.reserve((size_t)qpad * sizeof(double)));
     TC_TRY(sc.q_err.reserve((size_t)qpad * sizeof(double)));
     TC_TRY(sc.cand_val.reserve((size_t)qpad * nslot * kprime * sizeof(float)));
@@ -1554,8 +1616,8 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     TC_TRY(sc.fb_count.reserve(sizeof(int)));
 
     const int64_t threads = qpad * 32;
-    tc_prep_rows_kernel<false><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
-        d_queries, q, qpad, d, st.dp, st.center.as<float>(), nullptr, sc.q_bf16.as<__nv_bfloat16>(),
+    (st.f16 ? tc_prep_rows_kernel<false, true> : tc_prep_rows_kernel<false, false>)<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+        d_queries, q, qpad, d, st.dp, st.center.as<float>(), st.scale, nullptr, sc.q_bf16.as<tc_elem>(),
         sc.q_norm2.as<double>(), sc.q_err.as<double>(), nullptr, nullptr);
     ++*launches;
     TC_TRY(cudaGetLastError());
@@ -1566,7 +1628,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
 
     TcParams p;
     p.nkb = nkb; p.ksteps = ksteps; p.nqt = nqt; p.nseg = nseg; p.nq_single = nq_single; p.tiles_per_seg = tiles_per_seg;
-    p.tiles_total = tiles_total; p.kprime = kprime; p.kactive = (tl.opt_active > 0 && tl.opt_active <= kprime) ? tl.opt_active : kprime; p.epi_warps = epi_warps; p.stages = stages; p.nslot = nslot; p.a_resident = a_resident ? 1 : 0;
+    p.tiles_total = tiles_total; p.kprime = kprime; p.f16 = st.f16 ? 1 : 0; p.kactive = (tl.opt_active > 0 && tl.opt_active <= kprime) ? tl.opt_active : kprime; p.epi_warps = epi_warps; p.stages = stages; p.nslot = nslot; p.a_resident = a_resident ? 1 : 0;
     p.cand_val = sc.cand_val.as<float>(); p.cand_idx = sc.cand_idx.as<int>();
     p.cand_thr = sc.cand_thr.as<float>();
     p.h = st.half_norm.as<float>(); p.hmin8 = st.hmin8.as<float>(); p.hblk = st.hblk.as<float>();
@@ -1610,7 +1672,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     if (tl.debug) return 0;   // profiling ablations: results are meaningless, skip rescoring
 
     TcBounds b;
-    b.et_max = st.et_max; b.tnorm_max = st.tnorm_max;
+    b.et_max = st.et_max; b.tnorm_max = st.tnorm_max; b.inv_scale = 1.0 / (double)st.scale;
     // (K + 8) * 2^-22 accumulation + 2^-22 for rounding h, subtracting it and the group test thr + min(h) +
     // 2^-17 for the slot bits packed into list values
     b.c_mma = (double)(ksteps * 16 + 8) * 2.384185791015625e-07 + 2.4e-7 + 7.62939453125e-06;
@@ -1632,6 +1694,8 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, st.ev_k1_begin, st.ev_k1_end) == cudaSuccess) st.filter_ms += ms;
     }
+    // many unproven queries mean the bf16 rounding residuals are too large for this data: use fp16 from the next call on
+    if (level == 0 && !st.f16 && tl.opt_precision == 0 && q >= 4096 && (int64_t)count * 400 > q) st.want_f16 = true;
     if (count > 0) {
         TC_TRY(sc.fb_queries.reserve((size_t)count * d * sizeof(float)));
         TC_TRY(sc.fb_d.reserve((size_t)count * ksel * sizeof(float)));

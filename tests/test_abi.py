@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(_native.LIB_PATH)
     for name in _declared_symbols():
         assert getattr(raw, name) is not None
-    assert lib.osml_knn_abi_version() == 1002
+    assert lib.osml_knn_abi_version() == 1003
 
 
 def test_enum_values_match_the_header():

@@ -232,3 +232,47 @@ def test_more_queries_than_one_block():
     ix.close()
     assert np.array_equal(idx, d_idx) and np.array_equal(dist, d_dist) and np.array_equal(pred, d_pred)
     assert stats['tensor_queries'] == q
+
+
+@pytest.mark.parametrize('precision', [1, 2])
+def test_both_filter_precisions_are_exact(precision):
+    """The filter copy is bf16 (precision=1) or scaled fp16 (precision=2); either way the result is the exact one."""
+    rng = np.random.default_rng(41)
+    n, d, q, k = 120000, 96, 4000, 32
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32) * 3 + 7)
+    test = rng.standard_normal((q, d), dtype=np.float32) * 3 + 7
+    labels = rng.integers(0, 5, n)
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    ix.set_option('path', _native.PATH_TENSOR)
+    ix.set_option('precision', precision)
+    pred, idx, dist = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    stats = ix.stats()
+    assert stats['filter_precision'] == precision
+    ix.set_option('path', _native.PATH_DIRECT)
+    d_pred, d_idx, d_dist = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    ix.close()
+    assert np.array_equal(idx, d_idx) and np.array_equal(dist, d_dist) and np.array_equal(pred, d_pred)
+    if precision == 2:                       # 8x smaller rounding residuals: (almost) nothing left for the second pass
+        assert stats['retry_queries'] <= q // 200, stats
+
+
+def test_precision_switches_to_fp16_when_bf16_needs_many_second_passes():
+    """Auto mode starts with bf16; a call in which more than 0.25 % of the queries needed the second pass makes the next
+    call rebuild the filter copy in fp16.  Results are identical before and after."""
+    rng = np.random.default_rng(42)
+    centres = rng.standard_normal((40, 64)).astype(np.float32) * 30
+    train = np.asfortranarray(centres[rng.integers(0, 40, 50000)] +
+                              0.05 * rng.standard_normal((50000, 64)).astype(np.float32))
+    test = centres[rng.integers(0, 40, 6000)] + 0.05 * rng.standard_normal((6000, 64)).astype(np.float32)
+    labels = rng.integers(0, 5, 50000)
+    ix = _native.Index(train, labels, 10, 1, 1e-8)
+    ix.set_option('path', _native.PATH_TENSOR)
+    first = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    stats_first = ix.stats()
+    second = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    stats_second = ix.stats()
+    ix.close()
+    for a, b in zip(first, second):
+        assert np.array_equal(a, b)
+    assert stats_first['filter_precision'] == 1 and stats_first['retry_queries'] > len(test) // 400, stats_first
+    assert stats_second['filter_precision'] == 2, stats_second
