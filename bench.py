@@ -237,6 +237,8 @@ def run_ours(args):
     q = queries.shape[0]
     index = _native.Index(train, labels, k, 1, 1e-8, device=local_rank)      # = KNearestNeighbors._fit
     index.set_option('path', _native.PATHS[args.path])
+    if args.no_pipeline:
+        index.set_option('pipeline', 0)
 
     stream = torch.cuda.current_stream().cuda_stream
     d_queries = torch.from_numpy(queries).cuda()
@@ -338,7 +340,9 @@ def run_ours(args):
             'config': workload_description(args.workload, n_gpus),
             'e2e': {'value': e2e_value, 'unit': 'queries/s', 'h2d_bytes_per_step': int(queries.nbytes),
                     'd2h_bytes_per_step': int(q * 8), 'ms_per_step': e2e_ms / args.steps,
-                    'api': 'osml_knn_predict (C ABI, pinned host buffers)'},
+                    'api': 'osml_knn_predict (C ABI, pinned host buffers)',
+                    'upload': 'whole matrix first' if args.no_pipeline else
+                              'two blocks, the second under the first block\'s filter kernel'},
             'gpu_launches': int(launches), 'roofline': roofline,
             'cpu_baseline': cpu_baseline,
             'clocks': clocks, 'retry_queries_per_step': retried / args.steps,
@@ -471,6 +475,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS) + ['c5'])
     ap.add_argument('--path', default='auto', choices=['auto', 'direct', 'tensor'])
+    ap.add_argument('--no-pipeline', action='store_true',
+                    help='A/B: osml_knn_predict uploads the whole query matrix before the first kernel')
     args = ap.parse_args()
     if args.workload == 'c5':
         if args.impl == 'reference':

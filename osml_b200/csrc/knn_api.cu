@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <string>
 #include <vector>
@@ -101,6 +102,10 @@ struct osml_knn_index {
     int debug = 0;
     int counters = 0;
     int64_t query_block = 0;
+    int opt_pipeline = 1;      // osml_knn_predict: 1 = upload the tail of a large query matrix under the first block's K1
+    int sm_count = 0;
+    const std::function<int()>* before_wait = nullptr;   // both set only while a pipelined osml_knn_predict is in flight
+    int64_t first_block = 0;
 
     DeviceBuffer train;        // row-major n x d, original dtype
     DeviceBuffer label_bits;   // int64 per label
@@ -114,6 +119,8 @@ struct osml_knn_index {
     osml::TensorState tensor;  // K0/K1/K3 state (bf16 copy, norms, tensor maps, scratch)
 
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // second block's upload (pipelined osml_knn_predict)
+    cudaEvent_t ev_copy = nullptr, ev_first = nullptr;   // second block uploaded / first block uploaded
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     osml_knn_stats stats{};
 
@@ -146,6 +153,34 @@ int upload_matrix(osml_knn_index* ix, const void* host, int layout, int64_t rows
         case 2: transpose_colmajor_kernel<uint16_t><<<grid, block, 0, stream>>>(ix->stage.as<uint16_t>(), dst.as<uint16_t>(), rows, cols); break;
         case 4: transpose_colmajor_kernel<uint32_t><<<grid, block, 0, stream>>>(ix->stage.as<uint32_t>(), dst.as<uint32_t>(), rows, cols); break;
         default: transpose_colmajor_kernel<uint64_t><<<grid, block, 0, stream>>>(ix->stage.as<uint64_t>(), dst.as<uint64_t>(), rows, cols); break;
+    }
+    ix->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return OSML_KNN_OK;
+}
+
+// Rows [r0, r1) of a host matrix of `rows` rows into the same rows of the row-major device matrix `dst` (already
+// reserved for all rows).  Column-major input goes through its own region of the staging buffer (already reserved) as a
+// pitched copy and is transposed on the same stream, so blocks on different streams do not touch each other's memory.
+int upload_rows(osml_knn_index* ix, const void* host, int layout, int64_t rows, int64_t cols, int64_t r0, int64_t r1,
+                DeviceBuffer& dst, cudaStream_t stream) {
+    const size_t es = dtype_size(ix->dtype);
+    const int64_t nr = r1 - r0;
+    char* out = dst.as<char>() + (size_t)r0 * cols * es;
+    if (layout == OSML_KNN_ROW_MAJOR || rows == 1 || cols == 1) {
+        CUDA_TRY(cudaMemcpyAsync(out, static_cast<const char*>(host) + (size_t)r0 * cols * es, (size_t)nr * cols * es,
+                                 cudaMemcpyHostToDevice, stream));
+        return OSML_KNN_OK;
+    }
+    char* st = ix->stage.as<char>() + (size_t)r0 * cols * es;      // [cols][nr], element (i, j) at j * nr + i
+    CUDA_TRY(cudaMemcpy2DAsync(st, (size_t)nr * es, static_cast<const char*>(host) + (size_t)r0 * es, (size_t)rows * es,
+                               (size_t)nr * es, (size_t)cols, cudaMemcpyHostToDevice, stream));
+    dim3 block(32, 8), grid((unsigned)((nr + 31) / 32), (unsigned)((cols + 31) / 32));
+    switch (es) {
+        case 1: transpose_colmajor_kernel<uint8_t><<<grid, block, 0, stream>>>((const uint8_t*)st, (uint8_t*)out, nr, cols); break;
+        case 2: transpose_colmajor_kernel<uint16_t><<<grid, block, 0, stream>>>((const uint16_t*)st, (uint16_t*)out, nr, cols); break;
+        case 4: transpose_colmajor_kernel<uint32_t><<<grid, block, 0, stream>>>((const uint32_t*)st, (uint32_t*)out, nr, cols); break;
+        default: transpose_colmajor_kernel<uint64_t><<<grid, block, 0, stream>>>((const uint64_t*)st, (uint64_t*)out, nr, cols); break;
     }
     ix->stats.kernel_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -288,6 +323,7 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         tl.sum_order = ix->sum_order; tl.index_base = ix->index_base; tl.slack = ix->slack;
         tl.opt_epi_warps = ix->opt_epi_warps; tl.opt_nseg = ix->opt_nseg; tl.debug = ix->debug; tl.counters = ix->counters;
         tl.opt_smem_lists = ix->opt_smem_lists; tl.opt_cta_group = ix->opt_cta_group; tl.opt_active = ix->opt_active; tl.opt_precision = ix->opt_precision;
+        tl.before_wait = ix->before_wait; tl.first_block = ix->first_block;
         int64_t fallback = 0, launches = 0;
         std::string err;
         int rc = osml::tensor_neighbours(ix->tensor, tl, d_queries, q, out_d, out_i, stream, &fallback, &launches, &err,
@@ -378,6 +414,10 @@ int osml_knn_create(osml_knn_index** out, int device, const void* train, int dty
         return cleanup(fail(OSML_KNN_EUNSUPPORTED, "unsupported label dtype"));
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ix->ev_copy, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ix->ev_first, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
         (e = cudaEventCreate(&ix->ev0)) != cudaSuccess || (e = cudaEventCreate(&ix->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&ix->ev2)) != cudaSuccess || (e = cudaEventCreate(&ix->ev3)) != cudaSuccess)
         return cleanup(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
@@ -404,6 +444,9 @@ int osml_knn_destroy(osml_knn_index* ix) {
     if (ix->ev1) cudaEventDestroy(ix->ev1);
     if (ix->ev2) cudaEventDestroy(ix->ev2);
     if (ix->ev3) cudaEventDestroy(ix->ev3);
+    if (ix->ev_copy) cudaEventDestroy(ix->ev_copy);
+    if (ix->ev_first) cudaEventDestroy(ix->ev_first);
+    if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
     return OSML_KNN_OK;
@@ -493,19 +536,52 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
     if (layout != OSML_KNN_ROW_MAJOR && layout != OSML_KNN_COL_MAJOR) return fail(OSML_KNN_EINVAL, "bad layout");
     DeviceGuard guard(ix->device);
     const size_t ksel = (size_t)ix->ksel();
-    CUDA_TRY(cudaEventRecord(ix->ev0, ix->stream));
-    rc = upload_matrix(ix, queries, layout, q, ix->d, ix->queries, ix->stream);
-    if (rc != OSML_KNN_OK) return rc;
+    const size_t es = dtype_size(ix->dtype);
+    CUDA_TRY(ix->queries.reserve((size_t)q * ix->d * es));
+    if (layout == OSML_KNN_COL_MAJOR && q > 1 && ix->d > 1) CUDA_TRY(ix->stage.reserve((size_t)q * ix->d * es));
     CUDA_TRY(ix->nn_d.reserve((size_t)q * ksel * ix->dist_size()));
     CUDA_TRY(ix->nn_i.reserve((size_t)q * ksel * 8));
     CUDA_TRY(ix->pred.reserve((size_t)q * 8));
-    if (ix->has_q_transform) {            // raw queries: Centering / Standardization on the device, in place
-        rc = apply_query_transform(ix, ix->queries.ptr, ix->queries.ptr, q, ix->stream);
-        if (rc != OSML_KNN_OK) return rc;
+    // Pipelined upload: queries are independent, so a large matrix goes up in two blocks.  The first is one full wave of
+    // K1 work items (sm_count x 128 queries: every CTA pair sweeps one tile pair, nothing is split); the rest is copied on
+    // a second stream once the first block's kernels are queued, i.e. under its K1, instead of in front of everything.
+    const int64_t wave = (int64_t)ix->sm_count * 128;
+    const bool pipelined = ix->opt_pipeline && wave > 0 && q >= 2 * wave && use_tensor_path(ix, wave);
+    const int64_t qa = pipelined ? wave : q;
+    CUDA_TRY(cudaEventRecord(ix->ev0, ix->stream));
+    auto transform_rows = [&](int64_t r0, int64_t r1) -> int {   // raw queries: Centering / Standardization in place
+        if (!ix->has_q_transform) return OSML_KNN_OK;
+        char* dq = ix->queries.as<char>() + (size_t)r0 * ix->d * es;
+        return apply_query_transform(ix, dq, dq, r1 - r0, ix->stream);
+    };
+    rc = upload_rows(ix, queries, layout, q, ix->d, 0, qa, ix->queries, ix->stream);
+    if (rc == OSML_KNN_OK) rc = transform_rows(0, qa);
+    if (rc != OSML_KNN_OK) return rc;
+    bool sent = false;
+    const std::function<int()> send_rest = [&]() -> int {
+        if (sent) return OSML_KNN_OK;
+        sent = true;
+        CUDA_TRY(cudaStreamWaitEvent(ix->copy_stream, ix->ev_first, 0));   // the first block keeps the whole link
+        int rc2 = upload_rows(ix, queries, layout, q, ix->d, qa, q, ix->queries, ix->copy_stream);
+        if (rc2 != OSML_KNN_OK) return rc2;
+        CUDA_TRY(cudaEventRecord(ix->ev_copy, ix->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(ix->stream, ix->ev_copy, 0));
+        return transform_rows(qa, q);
+    };
+    if (pipelined) {
+        CUDA_TRY(cudaEventRecord(ix->ev_first, ix->stream));
+        ix->before_wait = &send_rest;
+        ix->first_block = qa;
     }
     rc = predict_device_impl(ix, ix->queries.ptr, q, task, ix->pred.as<double>(), ix->nn_i.as<int64_t>(), ix->nn_d.ptr,
                              ix->stream);
-    if (rc != OSML_KNN_OK) return rc;
+    ix->before_wait = nullptr;
+    ix->first_block = 0;
+    if (rc != OSML_KNN_OK) {
+        if (sent) cudaStreamSynchronize(ix->copy_stream);      // the caller's buffer must not be read after we return
+        return rc;
+    }
+    if (pipelined && !sent) return fail(OSML_KNN_ECUDA, "internal: the second block of queries was never uploaded");
     CUDA_TRY(cudaMemcpyAsync(out_pred, ix->pred.ptr, (size_t)q * 8, cudaMemcpyDeviceToHost, ix->stream));
     if (out_idx) CUDA_TRY(cudaMemcpyAsync(out_idx, ix->nn_i.ptr, (size_t)q * ksel * 8, cudaMemcpyDeviceToHost, ix->stream));
     if (out_dist)
@@ -657,6 +733,7 @@ int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
         return OSML_KNN_OK;
     }
     if (key == "query_block") { ix->query_block = (int64_t)value; return OSML_KNN_OK; }
+    if (key == "pipeline") { ix->opt_pipeline = value != 0.0; return OSML_KNN_OK; }
     return fail(OSML_KNN_EINVAL, "unknown option: " + key);
 }
 

@@ -1280,10 +1280,11 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
 }
 
 // ---- fallback plumbing ------------------------------------------------------------------------------------------------
-__global__ void tc_compact_flags_kernel(const int* __restrict__ flags, int64_t q_count, int* __restrict__ list,
-                                        int* __restrict__ count) {
+// appends the flagged queries of one block (block-local flags, first query = q_offset of the call) to the call's list
+__global__ void tc_compact_flags_kernel(const int* __restrict__ flags, int64_t q_count, int64_t q_offset,
+                                        int* __restrict__ list, int* __restrict__ count) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < q_count && flags[q]) list[atomicAdd(count, 1)] = (int)q;
+    if (q < q_count && flags[q]) list[atomicAdd(count, 1)] = (int)(q + q_offset);
 }
 
 __global__ void tc_gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ list, int count, int d,
@@ -1353,7 +1354,8 @@ struct TensorState {
     void* encode_fn = nullptr;
     int sm_count = 0;
     int smem_optin = 0;
-    cudaEvent_t ev_k1_begin = nullptr, ev_k1_end = nullptr;
+    std::vector<cudaEvent_t> ev_k1;   // (begin, end) per level-0 K1 launch of the call in flight
+    int ev_k1_used = 0;
     double filter_ms = 0.0;       // device time of the K1 launches of the last neighbour search (CUDA events)
     int64_t filter_launches = 0;
 };
@@ -1368,6 +1370,10 @@ struct TensorLaunch {
     int opt_precision = 0;   // 0 = auto (bf16, fp16 once a call needed many second passes), 1 = bf16, 2 = fp16
     int debug = 0;
     int counters = 0;        // 1 = the CTA-pair kernel records where its issuer / epilogue warps wait (printed to stderr)
+    // host work to issue once the first block's kernels are queued (the pipelined osml_knn_predict uploads the rest of
+    // the queries here, so the copy runs under the first block's K1); 0 = ok, else a status
+    const std::function<int()>* before_wait = nullptr;
+    int64_t first_block = 0; // > 0: the first block of the call has this many queries (the rest is not on the device yet)
 };
 
 using DirectFallback = std::function<int(const void*, int64_t, void*, int64_t*)>;
@@ -1403,9 +1409,9 @@ inline void tensor_release(TensorState& s) {
         b->release();
     s.scratch[0].release();
     s.scratch[1].release();
-    if (s.ev_k1_begin) cudaEventDestroy(s.ev_k1_begin);
-    if (s.ev_k1_end) cudaEventDestroy(s.ev_k1_end);
-    s.ev_k1_begin = s.ev_k1_end = nullptr;
+    for (cudaEvent_t e : s.ev_k1) cudaEventDestroy(e);
+    s.ev_k1.clear();
+    s.ev_k1_used = 0;
     s.ready = false;
 }
 
@@ -1538,10 +1544,12 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
     return 0;
 }
 
-// neighbour search for one block of queries (device, row-major fp32).  out_d/out_i: [q][k+1] final lists.
-inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
-                               float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
-                               int64_t* launches, std::string* err, const DirectFallback& direct, int level = 0) {
+// Filter + rescoring of one block of queries (device, row-major fp32), queued on `stream` without waiting for anything.
+// out_d/out_i: the block's [q][k+1] final lists.  Queries K3 could not prove are appended (as q_offset + local number) to
+// the level's fb_list / fb_count, which the caller reserved and zeroed; tc_resolve_unproven deals with them afterwards.
+inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
+                           float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* launches, std::string* err,
+                           int level, int64_t q_offset) {
     TensorState::Scratch& sc = st.scratch[level];
     const int d = (int)tl.d;
     const int ksel = tl.k + 1;
@@ -1612,8 +1620,6 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     TC_TRY(sc.cand_idx.reserve((size_t)qpad * nslot * kprime * sizeof(int)));
     TC_TRY(sc.cand_thr.reserve((size_t)qpad * nslot * sizeof(float)));
     TC_TRY(sc.flags.reserve((size_t)q * sizeof(int)));
-    TC_TRY(sc.fb_list.reserve((size_t)q * sizeof(int)));
-    TC_TRY(sc.fb_count.reserve(sizeof(int)));
 
     const int64_t threads = qpad * 32;
     (st.f16 ? tc_prep_rows_kernel<false, true> : tc_prep_rows_kernel<false, false>)<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
@@ -1645,11 +1651,17 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     TC_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nitems = nq_single + (nq_units - nq_single) * nseg;
     const int grid = tc_cta_group * std::min(nitems, st.sm_count / tc_cta_group);
-    if (!st.ev_k1_begin) { TC_TRY(cudaEventCreate(&st.ev_k1_begin)); TC_TRY(cudaEventCreate(&st.ev_k1_end)); }
+    if (level == 0 && (size_t)st.ev_k1_used + 2 > st.ev_k1.size()) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        TC_TRY(cudaEventCreate(&e0));
+        st.ev_k1.push_back(e0);
+        TC_TRY(cudaEventCreate(&e1));
+        st.ev_k1.push_back(e1);
+    }
     TC_TRY(cudaMemsetAsync(sc.cand_thr.ptr, 0xFF, (size_t)qpad * nslot * sizeof(float), stream));   // NaN bits: "not written"
-    if (level == 0) TC_TRY(cudaEventRecord(st.ev_k1_begin, stream));
+    if (level == 0) TC_TRY(cudaEventRecord(st.ev_k1[st.ev_k1_used], stream));
     kernel<<<grid, kTcThreads, smem, stream>>>(map_a, tc_cta_group == 2 ? st.map_b_half : st.map_b, p);
-    if (level == 0) TC_TRY(cudaEventRecord(st.ev_k1_end, stream));
+    if (level == 0) { TC_TRY(cudaEventRecord(st.ev_k1[st.ev_k1_used + 1], stream)); st.ev_k1_used += 2; }
     ++*launches;
     if (level == 0) ++st.filter_launches;
     TC_TRY(cudaGetLastError());
@@ -1677,22 +1689,40 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     // 2^-17 for the slot bits packed into list values
     b.c_mma = (double)(ksteps * 16 + 8) * 2.384185791015625e-07 + 2.4e-7 + 7.62939453125e-06;
     b.gamma = (double)(d + 4) * 1.1920928955078125e-07;                      // (D + 4) * 2^-23
-    TC_TRY(cudaMemsetAsync(sc.fb_count.ptr, 0, sizeof(int), stream));
     knn_rescore_kernel<<<(unsigned)((q + kRescoreWarps - 1) / kRescoreWarps), 32 * kRescoreWarps, 0, stream>>>(
         static_cast<const float*>(tl.train), tl.n, d_queries, d, tl.sum_order, q, ksel, sc.cand_val.as<float>(),
         sc.cand_idx.as<int>(), sc.cand_thr.as<float>(), st.perm.as<int>(), st.npad, nslot,
         (int64_t)nq_single * kTcBM * tc_cta_group, halves, kprime, sc.q_norm2.as<double>(), sc.q_err.as<double>(), b, tl.index_base, out_d,
         out_i, sc.flags.as<int>());
-    tc_compact_flags_kernel<<<(unsigned)((q + 255) / 256), 256, 0, stream>>>(sc.flags.as<int>(), q, sc.fb_list.as<int>(),
-                                                                             sc.fb_count.as<int>());
+    tc_compact_flags_kernel<<<(unsigned)((q + 255) / 256), 256, 0, stream>>>(sc.flags.as<int>(), q, q_offset,
+                                                                             sc.fb_list.as<int>(), sc.fb_count.as<int>());
     *launches += 2;
     TC_TRY(cudaGetLastError());
+    return 0;
+}
+
+inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
+                               float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
+                               int64_t* launches, std::string* err, const DirectFallback& direct, int level);
+
+// Waits for the blocks queued so far and settles the queries on the level's fb_list (numbers relative to d_queries /
+// out_d / out_i): level 0 re-runs them through a much finer filter pass, level 1 hands them to the exact direct kernel.
+inline int tc_resolve_unproven(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
+                               float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
+                               int64_t* launches, std::string* err, const DirectFallback& direct, int level) {
+    TensorState::Scratch& sc = st.scratch[level];
+    const int d = (int)tl.d;
+    const int ksel = tl.k + 1;
+    int rc = 0;
     int count = 0;
     TC_TRY(cudaMemcpyAsync(&count, sc.fb_count.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
     TC_TRY(cudaStreamSynchronize(stream));
     if (level == 0) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, st.ev_k1_begin, st.ev_k1_end) == cudaSuccess) st.filter_ms += ms;
+        for (int e = 0; e + 1 < st.ev_k1_used; e += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, st.ev_k1[e], st.ev_k1[e + 1]) == cudaSuccess) st.filter_ms += ms;
+        }
+        st.ev_k1_used = 0;
     }
     // many unproven queries mean the bf16 rounding residuals are too large for this data: use fp16 from the next call on
     if (level == 0 && !st.f16 && tl.opt_precision == 0 && q >= 4096 && (int64_t)count * 400 > q) st.want_f16 = true;
@@ -1703,7 +1733,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
         tc_gather_rows_kernel<<<count, 128, 0, stream>>>(d_queries, sc.fb_list.as<int>(), count, d,
                                                          sc.fb_queries.as<float>());
         ++*launches;
-        if (level == 0 && !tl.debug) {
+        if (level == 0) {
             // second chance on the filter: the same kernels over the few unproven queries, cut into as many train
             // segments as K3 can take -- every (segment, half) slot keeps its own K' best, so the kept set reaches
             // many times deeper and the proof almost always goes through.  Whatever still fails goes to K2 from there.
@@ -1725,6 +1755,25 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const fl
     return 0;
 }
 
+inline int tc_begin_unproven_list(TensorState& st, int level, int64_t q, cudaStream_t stream, std::string* err) {
+    TensorState::Scratch& sc = st.scratch[level];
+    TC_TRY(sc.fb_list.reserve((size_t)q * sizeof(int)));
+    TC_TRY(sc.fb_count.reserve(sizeof(int)));
+    TC_TRY(cudaMemsetAsync(sc.fb_count.ptr, 0, sizeof(int), stream));
+    return 0;
+}
+
+// one block, start to finish
+inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
+                               float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
+                               int64_t* launches, std::string* err, const DirectFallback& direct, int level) {
+    int rc = tc_begin_unproven_list(st, level, q, stream, err);
+    if (rc) return rc;
+    rc = tc_filter_block(st, tl, d_queries, q, out_d, out_i, stream, launches, err, level, 0);
+    if (rc || tl.debug) return rc;
+    return tc_resolve_unproven(st, tl, d_queries, q, out_d, out_i, stream, fallback, launches, err, direct, level);
+}
+
 inline int tensor_neighbours(TensorState& st, const TensorLaunch& tl, const void* d_queries, int64_t q, void* out_d,
                              int64_t* out_i, cudaStream_t stream, int64_t* fallback, int64_t* launches,
                              std::string* err, const DirectFallback& direct) {
@@ -1733,19 +1782,40 @@ inline int tensor_neighbours(TensorState& st, const TensorLaunch& tl, const void
     st.filter_ms = 0.0;
     st.filter_launches = 0;
     if (!st.usable) {                       // non-finite train rows: the filter's bounds do not hold
+        if (tl.before_wait && *tl.before_wait) {
+            rc = (*tl.before_wait)();
+            if (rc) return rc;
+        }
         *fallback += q;
         return direct(d_queries, q, out_d, out_i);
     }
+    // Blocks of queries are queued back to back and the host waits once, at the end, for the count of unproven queries
+    // of the whole call.  With a first_block the caller's before_wait hook runs as soon as that block is queued: the
+    // pipelined osml_knn_predict uploads the rest of the queries there (and makes `stream` wait for them).
     const int64_t block = 131072;
     const int ksel = tl.k + 1;
-    for (int64_t q0 = 0; q0 < q; q0 += block) {
-        const int64_t qb = std::min(block, q - q0);
-        rc = tc_neighbours_block(st, tl, static_cast<const float*>(d_queries) + q0 * tl.d, qb,
-                                 static_cast<float*>(out_d) + q0 * ksel, out_i + q0 * ksel, stream, fallback, launches,
-                                 err, direct);
+    const float* dq = static_cast<const float*>(d_queries);
+    float* od = static_cast<float*>(out_d);
+    rc = tc_begin_unproven_list(st, 0, q, stream, err);
+    if (rc) return rc;
+    st.ev_k1_used = 0;
+    int64_t q0 = 0;
+    if (tl.first_block > 0 && tl.first_block < q) {
+        rc = tc_filter_block(st, tl, dq, tl.first_block, od, out_i, stream, launches, err, 0, 0);
+        if (rc) return rc;
+        q0 = tl.first_block;
+    }
+    if (tl.before_wait && *tl.before_wait) {
+        rc = (*tl.before_wait)();
         if (rc) return rc;
     }
-    return 0;
+    for (; q0 < q; q0 += block) {
+        const int64_t qb = std::min(block, q - q0);
+        rc = tc_filter_block(st, tl, dq + q0 * tl.d, qb, od + q0 * ksel, out_i + q0 * ksel, stream, launches, err, 0, q0);
+        if (rc) return rc;
+    }
+    if (tl.debug) return 0;
+    return tc_resolve_unproven(st, tl, dq, q, od, out_i, stream, fallback, launches, err, direct, 0);
 }
 
 }  // namespace osml

@@ -276,3 +276,59 @@ def test_precision_switches_to_fp16_when_bf16_needs_many_second_passes():
         assert np.array_equal(a, b)
     assert stats_first['filter_precision'] == 1 and stats_first['retry_queries'] > len(test) // 400, stats_first
     assert stats_second['filter_precision'] == 2, stats_second
+
+
+@pytest.mark.parametrize('order', ['C', 'F'])
+@pytest.mark.parametrize('fused_transform', [False, True])
+def test_pipelined_upload_equals_the_single_block_call(order, fused_transform):
+    """osml_knn_predict sends a large query matrix up in two blocks (one wave of K1 work items, then the rest on a
+    second stream under the first block's K1).  Row- and column-major host buffers, with and without the fused query
+    transform, ragged tail: everything must equal the unpipelined call bit for bit."""
+    rng = np.random.default_rng(51)
+    n, d, q, k = 20000, 24, 2 * 148 * 128 + 3331, 6
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = np.asarray(rng.standard_normal((q, d), dtype=np.float32) * 1.5 + 0.25, order=order)
+    labels = rng.integers(0, 7, n)
+    results = []
+    for pipeline in (1, 0):
+        ix = _native.Index(train, labels, k, 1, 1e-8)
+        ix.set_option('path', _native.PATH_TENSOR)
+        ix.set_option('pipeline', pipeline)
+        if fused_transform:
+            ix.set_query_transform(np.full(d, 0.25, np.float32), np.full(d, 1.5, np.float32))
+        results.append(ix.predict(test, _native.CLASSIFICATION, return_neighbours=True))
+        # a second call reuses every buffer and stream
+        again = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+        assert all(np.array_equal(a, b) for a, b in zip(results[-1], again))
+        stats = ix.stats()
+        assert stats['tensor_queries'] == 2 * q
+        assert stats['last_filter_launches'] == (2 if pipeline else 1)
+        ix.close()
+    for a, b in zip(*results):
+        assert np.array_equal(a, b)
+    if not fused_transform:
+        sample = rng.choice(q, 64, replace=False)
+        pred, idx, dist = (r[sample] for r in results[0])
+        parity.assert_matches_oracle(pred, idx, dist, train, labels, np.ascontiguousarray(test[sample]), k, 1,
+                                     'classification')
+
+
+def test_unproven_queries_of_every_block_are_settled_in_one_pass_at_the_end():
+    """Three blocks in one call (the pipelined first wave, a full block of 131072, a ragged tail) on clustered data: each
+    block leaves unproven queries behind; they are collected with call-wide numbers and re-run once, after the last
+    block.  Result = the direct kernel's, bit for bit."""
+    rng = np.random.default_rng(61)
+    n, d, k = 40000, 32, 8
+    q = 148 * 128 + 131072 + 517
+    centres = rng.standard_normal((25, d)).astype(np.float32)
+    train = np.asfortranarray(centres[rng.integers(0, 25, n)] + 1e-3 * rng.standard_normal((n, d)).astype(np.float32))
+    test = centres[rng.integers(0, 25, q)] + 1e-3 * rng.standard_normal((q, d)).astype(np.float32)
+    labels = rng.integers(0, 5, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    assert stats['tensor_queries'] == q and stats['last_filter_launches'] == 3, stats
+    assert stats['retry_queries'] > 0, stats
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    ix.set_option('path', _native.PATH_DIRECT)
+    d_pred, d_idx, d_dist = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    ix.close()
+    assert np.array_equal(idx, d_idx) and np.array_equal(dist, d_dist) and np.array_equal(pred, d_pred)
