@@ -1,4 +1,5 @@
-"""ctypes binding of the C ABI in include/osml_knn.h (libosml_knn.so, built in-tree by osml_b200/build.py).
+"""ctypes binding of the C ABI in include/osml_knn.h and include/osml_svm.h (libosml_knn.so, built in-tree by
+osml_b200/build.py).
 
 This is the only door to the arithmetic of the path.  It fails loudly: a missing library raises ImportError with the
 build command, a non-zero status raises ValueError (where the reference raises ValueError) or RuntimeError.
@@ -30,6 +31,10 @@ SYMBOLS = ('osml_knn_create', 'osml_knn_destroy', 'osml_knn_predict', 'osml_knn_
            'osml_knn_neighbours_device', 'osml_knn_merge_predict_device', 'osml_knn_set_option',
            'osml_knn_get_stats', 'osml_knn_reset_stats', 'osml_knn_describe', 'osml_knn_last_error',
            'osml_knn_abi_version', 'osml_knn_column_transform', 'osml_knn_set_query_transform')
+# every symbol include/osml_svm.h declares
+SVM_SYMBOLS = ('osml_svm_create', 'osml_svm_destroy', 'osml_svm_set_multipliers', 'osml_svm_decision',
+               'osml_svm_decision_self', 'osml_svm_decision_device', 'osml_svm_get_stats')
+SVM_KERNELS = {'lin': 0, 'poly': 1, 'rbf': 2}
 
 
 class Stats(ctypes.Structure):
@@ -73,7 +78,15 @@ def lib():
     cdll.osml_knn_last_error.restype = ctypes.c_char_p
     cdll.osml_knn_last_error.argtypes = []
     cdll.osml_knn_abi_version.argtypes = []
-    for name in SYMBOLS:
+    cdll.osml_svm_create.argtypes = [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp, c_vp,
+                                     c_dbl, c_int, c_dbl, c_dbl, c_dbl]
+    cdll.osml_svm_destroy.argtypes = [c_vp]
+    cdll.osml_svm_set_multipliers.argtypes = [c_vp, c_vp, c_dbl]
+    cdll.osml_svm_decision.argtypes = [c_vp, c_vp, c_int, c_i64, c_vp]
+    cdll.osml_svm_decision_self.argtypes = [c_vp, c_vp]
+    cdll.osml_svm_decision_device.argtypes = [c_vp, c_vp, c_i64, c_vp, c_vp]
+    cdll.osml_svm_get_stats.argtypes = [c_vp, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64)]
+    for name in SYMBOLS + SVM_SYMBOLS:
         if name not in ('osml_knn_last_error',):
             getattr(cdll, name).restype = c_int
     _lib = cdll
@@ -239,3 +252,72 @@ class Index:
                              d_out_dist=None, stream=None):
         check(lib().osml_knn_merge_predict_device(self._handle, d_part_idx, d_part_dist, int(parts), int(q),
                                                   int(task), d_out_pred, d_out_idx, d_out_dist, stream))
+
+
+class Machine:
+    """Owner of one ``osml_svm_machine`` handle (include/osml_svm.h): vectors, -1 / +1 labels, multipliers and
+    intercept of a kernel machine on the GPU, and its decision function."""
+
+    def __init__(self, vectors, labels, alphas, intercept, kernel, gamma=.5, degree=2, poly_coefficient=1., device=0,
+                 sum_order=None):
+        self._handle = ctypes.c_void_p()
+        vectors = np.asarray(vectors)
+        if vectors.ndim != 2:
+            raise ValueError
+        if sum_order is None:
+            sum_order = sum_order_of(vectors)
+        mat, layout = matrix_layout(vectors)
+        labels = np.ascontiguousarray(labels, dtype=np.float64)
+        alphas = np.ascontiguousarray(alphas, dtype=np.float64)
+        self.dtype = mat.dtype
+        self.n, self.d = int(mat.shape[0]), int(mat.shape[1])
+        if labels.shape != (self.n,) or alphas.shape != (self.n,):
+            raise ValueError
+        if kernel not in SVM_KERNELS:
+            raise ValueError
+        self.device = int(device)
+        check(lib().osml_svm_create(ctypes.byref(self._handle), self.device, mat.ctypes.data, dtype_code(mat.dtype),
+                                    layout, self.n, self.d, int(sum_order), labels.ctypes.data, alphas.ctypes.data,
+                                    float(intercept), SVM_KERNELS[kernel], float(gamma), float(degree),
+                                    float(poly_coefficient)))
+
+    def close(self):
+        if getattr(self, '_handle', None) is not None and self._handle.value:
+            lib().osml_svm_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_multipliers(self, alphas, intercept):
+        alphas = np.ascontiguousarray(alphas, dtype=np.float64)
+        if alphas.shape != (self.n,):
+            raise ValueError
+        check(lib().osml_svm_set_multipliers(self._handle, alphas.ctypes.data, float(intercept)))
+
+    def decision(self, queries):
+        """Host matrix in, float64 decision values out (osml_svm_decision)."""
+        queries = np.asarray(queries)
+        if queries.ndim != 2 or queries.shape[1] != self.d or queries.dtype != self.dtype:
+            raise ValueError
+        mat, layout = matrix_layout(queries)
+        out = np.empty(mat.shape[0], dtype=np.float64)
+        check(lib().osml_svm_decision(self._handle, mat.ctypes.data, layout, int(mat.shape[0]), out.ctypes.data))
+        return out
+
+    def decision_self(self):
+        """Decision value of every vector of the machine against the machine (osml_svm_decision_self)."""
+        out = np.empty(self.n, dtype=np.float64)
+        check(lib().osml_svm_decision_self(self._handle, out.ctypes.data))
+        return out
+
+    def decision_device(self, d_queries, q, d_out, stream=None):
+        check(lib().osml_svm_decision_device(self._handle, d_queries, int(q), d_out, stream))
+
+    def stats(self):
+        ms, launches = ctypes.c_double(), ctypes.c_int64()
+        check(lib().osml_svm_get_stats(self._handle, ctypes.byref(ms), ctypes.byref(launches)))
+        return {'last_kernel_ms': ms.value, 'kernel_launches': launches.value}

@@ -764,3 +764,5 @@ int osml_knn_describe(osml_knn_index* ix, int64_t* n, int64_t* d, int* k, int* d
 }
 
 }  // extern "C"
+
+#include "svm_api.cuh"
