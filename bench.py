@@ -323,6 +323,31 @@ def run_ours(args):
         roofline = {'bound': 'hbm', 'achieved': None, 'peak': peak_gbs, 'unit': 'GB/s', 'frac': None, 'traffic': None,
                     'note': 'direct (K2) path is CUDA-core bound: 3 un-fusable instructions per element'}
 
+    dataframe_api = None
+    if n_gpus == 1:
+        # the call a user of the reference makes: model.predict(DataFrame) -> Series (pageable F-ordered frame values,
+        # validation and Series wrapping included); its own fitted model, same data
+        import pandas as pd
+        import osml_b200 as ob
+        index.close()
+        model = ob.KNearestNeighborsClassification(k=k)
+        model.path = args.path
+        model.fit(pd.DataFrame(train), pd.Series(labels, name='label'))
+        if args.no_pipeline:
+            model._index.set_option('pipeline', 0)
+        query_df = pd.DataFrame(queries)
+        for _ in range(2):
+            series = model.predict(query_df)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            series = model.predict(query_df)
+        df_ms = (time.perf_counter() - t0) * 1e3
+        assert np.array_equal(series.values.astype(np.float64), first_pred), 'model API and C ABI disagree'
+        dataframe_api = {'value': q * args.steps / (df_ms / 1e3), 'unit': 'queries/s', 'ms_per_step': df_ms / args.steps,
+                         'api': 'osml_b200.KNearestNeighborsClassification.predict(DataFrame) -> Series'}
+        model._drop_index()
+
     if n_gpus == 1:
         cpu_value, cpu_sample, cpu_pred = cpu_baseline_single_core(train, labels, queries, k)
         parity_ok = bool(np.array_equal(cpu_pred, first_pred[:cpu_sample]))
@@ -342,7 +367,8 @@ def run_ours(args):
                     'd2h_bytes_per_step': int(q * 8), 'ms_per_step': e2e_ms / args.steps,
                     'api': 'osml_knn_predict (C ABI, pinned host buffers)',
                     'upload': 'whole matrix first' if args.no_pipeline else
-                              'two blocks, the second under the first block\'s filter kernel'},
+                              'two blocks, the second under the first block\'s filter kernel',
+                    'dataframe_api': dataframe_api},
             'gpu_launches': int(launches), 'roofline': roofline,
             'cpu_baseline': cpu_baseline,
             'clocks': clocks, 'retry_queries_per_step': retried / args.steps,

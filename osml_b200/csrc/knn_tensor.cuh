@@ -59,6 +59,7 @@ constexpr int kTcBStageBytes = kTcBN * 128;   // 32 KB
 constexpr int kTcThreads = 384;       // warp 0 TMA, 1 MMA (3 too in the pair kernel), 2 TMEM alloc, 4..11 epilogue
 constexpr int kTcMaxKPrime = 64;
 constexpr int kTcMaxCand = 512;       // candidates per query K3 handles (slots * K')
+constexpr int kTcMaxCandRetry = 1024; // ... in the second filter pass (its own K3 instance, 2 queries per CTA)
 
 struct TcParams {
     int nkb;             // K blocks of the padded feature dimension
@@ -1132,6 +1133,7 @@ struct TcBounds {
 };
 
 constexpr int kRescoreWarps = 4;
+constexpr int kRescoreWarpsRetry = 2;
 
 // exact fp32 distance, 16-byte loads when the row length allows (same left-to-right order as sum_sequential)
 __device__ __forceinline__ float tc_exact_distance(const float* __restrict__ t, const float* __restrict__ q, int d,
@@ -1165,20 +1167,22 @@ __device__ __forceinline__ unsigned long long tc_score_key(float a, int c) {
     return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)c);   // ties: lowest position
 }
 
-__global__ void __launch_bounds__(32 * kRescoreWarps)
+template <int kCand, int kWarps>       // candidates per query the shared-memory lists hold; queries (= warps) per CTA
+__global__ void __launch_bounds__(32 * kWarps)
 knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __restrict__ queries, int d, int sum_order,
                    int64_t q_count, int ksel, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
                    const float* __restrict__ cand_thr, const int* __restrict__ perm, int64_t npad, int nslot,
                    int64_t q_single, int slots_single, int kprime, const double* __restrict__ qnorm2,
                    const double* __restrict__ qerr, TcBounds bounds, int64_t index_base, float* __restrict__ out_d,
                    int64_t* __restrict__ out_i, int* __restrict__ flags) {
-    __shared__ float s_acc[kRescoreWarps][kTcMaxCand];
-    __shared__ int s_idx[kRescoreWarps][kTcMaxCand];
-    __shared__ float s_dist[kRescoreWarps][kTcMaxCand];       // exact distances, by position in s_work
-    __shared__ short s_work[kRescoreWarps][kTcMaxCand];       // compacted candidate positions: selected, then the rest
-    __shared__ float s_best[kRescoreWarps];
+    static_assert(kCand <= 1024, "the per-lane `taken` mask has 32 bits");
+    __shared__ float s_acc[kWarps][kCand];
+    __shared__ int s_idx[kWarps][kCand];
+    __shared__ float s_dist[kWarps][kCand];       // exact distances, by position in s_work
+    __shared__ short s_work[kWarps][kCand];       // compacted candidate positions: selected, then the rest
+    __shared__ float s_best[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * kRescoreWarps + warp;
+    const int64_t q = (int64_t)blockIdx.x * kWarps + warp;
     if (q >= q_count) return;
     const float* cv = cand_val + (size_t)q * nslot * kprime;
     const int* ci = cand_idx + (size_t)q * nslot * kprime;
@@ -1211,7 +1215,7 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
     for (int off = 16; off > 0; off >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, off);
     __syncwarp();
     bool ok = nvalid >= ksel;
-    // pass 1: the k+1 best-scoring candidates, one warp arg-max round each (ncand <= 512: 16 entries per lane)
+    // pass 1: the k+1 best-scoring candidates, one warp arg-max round each (ncand <= 1024: at most 32 entries per lane)
     uint32_t taken = 0;                               // bit i: candidate lane + 32 * i already picked
     const int nsel = min(ksel, nvalid);
     for (int s = 0; s < nsel; ++s) {
@@ -1579,7 +1583,9 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const float*
     // first floor(T / U) * U tiles are single-item sweeps and only the remainder -- which would otherwise occupy a
     // fraction of the machine for a whole sweep -- is cut into nseg interleaved segments.  (Single-CTA kernels split
     // every tile the same way: nq_single = 0.)
-    const int max_seg_by_cand = std::max(1, kTcMaxCand / (kprime * halves));
+    // the second filter pass (level 1, a handful of queries) may cut finer: its K3 instance holds twice the candidates
+    const int cand_cap = level == 0 ? kTcMaxCand : kTcMaxCandRetry;
+    const int max_seg_by_cand = std::max(1, cand_cap / (kprime * halves));
     const int max_seg = std::max(1, std::min(max_seg_by_cand, std::max(1, tiles_total / 8)));
     const int units = std::max(1, st.sm_count / tc_cta_group);
     const int nq_units = nqt / tc_cta_group;                 // query tiles (single CTA) or tile pairs
@@ -1689,7 +1695,10 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const float*
     // 2^-17 for the slot bits packed into list values
     b.c_mma = (double)(ksteps * 16 + 8) * 2.384185791015625e-07 + 2.4e-7 + 7.62939453125e-06;
     b.gamma = (double)(d + 4) * 1.1920928955078125e-07;                      // (D + 4) * 2^-23
-    knn_rescore_kernel<<<(unsigned)((q + kRescoreWarps - 1) / kRescoreWarps), 32 * kRescoreWarps, 0, stream>>>(
+    const bool wide_k3 = nslot * kprime > kTcMaxCand;
+    const int k3_warps = wide_k3 ? kRescoreWarpsRetry : kRescoreWarps;
+    (wide_k3 ? knn_rescore_kernel<kTcMaxCandRetry, kRescoreWarpsRetry> : knn_rescore_kernel<kTcMaxCand, kRescoreWarps>)
+        <<<(unsigned)((q + k3_warps - 1) / k3_warps), 32 * k3_warps, 0, stream>>>(
         static_cast<const float*>(tl.train), tl.n, d_queries, d, tl.sum_order, q, ksel, sc.cand_val.as<float>(),
         sc.cand_idx.as<int>(), sc.cand_thr.as<float>(), st.perm.as<int>(), st.npad, nslot,
         (int64_t)nq_single * kTcBM * tc_cta_group, halves, kprime, sc.q_norm2.as<double>(), sc.q_err.as<double>(), b, tl.index_base, out_d,

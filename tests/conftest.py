@@ -15,7 +15,9 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and not f.startswith('transform_'))
+    # kNN fixtures; transform_* and svm_* have their own loaders (load_transform_golden, tests/test_oracle_svm.py)
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.endswith('.npz') and not f.startswith(('transform_', 'svm_')))
 
 
 def transform_golden_names():

@@ -75,14 +75,17 @@ def test_pairwise_feature_sum_of_c_ordered_vectors(dtype, d):
     want = so.raw_predict(queries, vectors, labels, alphas, .5, **args)
     _assert_close(machine.decision(queries), want, vectors, queries, alphas, .5, args)
     machine.close()
-    # one vector, multiplier 1, label 1, intercept 0: the decision value IS exp(-gamma * distance) in the data's dtype;
-    # with numpy's own summation order the distance is identical, so the values agree to the accuracy of the two exp
-    # implementations (CUDA expf: 2 ulp; numpy's SIMD float32 exp: 2.5 ulp)
+    # one vector, multiplier 1, label 1, intercept 0: the decision value IS exp(arg), arg = -gamma * distance in the
+    # data's dtype.  numpy gives the reference's arg; the exact exp of it (float64) must be within CUDA's documented
+    # error of exp (2 ulp float32, 1 ulp float64; + the rounding to dtype) -- a distance off by one ulp would move
+    # the result by |arg| ulps and more.
     one = _native.Machine(vectors[:1], np.ones(1), np.ones(1), 0., **args)
     got = one.decision(queries)
-    want = so.raw_predict(queries, vectors[:1], np.ones(1), np.ones(1), 0., **args)
-    ulp = np.spacing(np.abs(want).astype(dtype)).astype(np.float64)
-    assert np.all(np.abs(got - want) <= 4 * ulp)
+    arg = np.array([(-args['gamma'] * np.sqrt(np.square(vectors[:1] - x).sum(axis=1)))[0] for x in queries])
+    assert arg.dtype == dtype
+    exact = np.exp(arg.astype(np.float64))
+    ulp = np.spacing(exact.astype(dtype)).astype(np.float64)
+    assert np.all(np.abs(got - exact) <= 2.5 * ulp), float(np.max(np.abs(got - exact) / ulp))
     one.close()
 
 
