@@ -43,8 +43,10 @@ def sum_order_of(observations):
     if observations.ndim != 2:
         raise ValueError
     n, d = observations.shape
-    if d == 1 or n == 1:
+    if d == 1:
         return 'sequential'
+    if n == 1:          # a single row is contiguous along the features whatever its flags say: numpy's pairwise_sum
+        return 'pairwise'
     s0, s1 = (abs(s) for s in observations.strides)
     return 'sequential' if s0 <= s1 else 'pairwise'
 

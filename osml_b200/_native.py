@@ -128,8 +128,10 @@ def sum_order_of(values):
     subtraction result inherits the stride order of ``values``; feature by feature when axis 0 is the fast axis (the
     F-ordered ``DataFrame.values`` of pandas 3), numpy's pairwise tree when axis 1 is."""
     n, d = values.shape
-    if d == 1 or n == 1:
+    if d == 1:
         return SUM_SEQUENTIAL
+    if n == 1:          # a single row is contiguous along the features whatever its flags say: numpy's pairwise_sum
+        return SUM_PAIRWISE
     s0, s1 = (abs(s) for s in values.strides)
     return SUM_SEQUENTIAL if s0 <= s1 else SUM_PAIRWISE
 

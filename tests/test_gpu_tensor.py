@@ -332,3 +332,26 @@ def test_unproven_queries_of_every_block_are_settled_in_one_pass_at_the_end():
     d_pred, d_idx, d_dist = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
     ix.close()
     assert np.array_equal(idx, d_idx) and np.array_equal(dist, d_dist) and np.array_equal(pred, d_pred)
+
+
+@pytest.mark.parametrize('extra', [-1, 0, 1])
+def test_pipelined_upload_boundaries(extra):
+    """Two waves of K1 work items (2 x 148 x 128 queries on a B200) is where osml_knn_predict starts to upload in two
+    blocks: one query fewer (single block), exactly two waves (the second block is one full wave), one more."""
+    rng = np.random.default_rng(71 + extra)
+    n, d, k = 4096, 8, 3
+    q = 2 * 148 * 128 + extra
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = np.asfortranarray(rng.standard_normal((q, d), dtype=np.float32))
+    labels = rng.standard_normal(n)
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    ix.set_option('path', _native.PATH_TENSOR)
+    pred, idx, dist = ix.predict(test, _native.REGRESSION, return_neighbours=True)
+    launches = ix.stats()['last_filter_launches']
+    ix.set_option('path', _native.PATH_DIRECT)
+    d_pred, d_idx, d_dist = ix.predict(test, _native.REGRESSION, return_neighbours=True)
+    ix.close()
+    assert np.array_equal(idx, d_idx) and np.array_equal(dist, d_dist) and np.array_equal(pred, d_pred)
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert launches == (2 if q >= 2 * sms * 128 else 1)
