@@ -363,8 +363,8 @@ def run_ours(args):
             'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_description(args.workload, n_gpus),
-            'e2e': {'value': e2e_value, 'unit': 'queries/s', 'h2d_bytes_per_step': int(queries.nbytes),
-                    'd2h_bytes_per_step': int(q * 8), 'ms_per_step': e2e_ms / args.steps,
+            'e2e': {'value': e2e_value, 'unit': 'queries/s', 'h2d_bytes_per_step': int(queries.nbytes) * n_gpus,
+                    'd2h_bytes_per_step': int(q * 8) * n_gpus, 'ms_per_step': e2e_ms / args.steps,
                     'api': 'osml_knn_predict (C ABI, pinned host buffers)',
                     'upload': 'whole matrix first' if args.no_pipeline else
                               'two blocks, the second under the first block\'s filter kernel',
