@@ -125,8 +125,8 @@ int osml_knn_merge_predict_device(osml_knn_index* index, const int64_t* d_part_i
                                   double* d_out_pred, int64_t* d_out_idx, void* d_out_dist, void* stream);
 
 /* Options: "path" (enum osml_knn_path), "slack" (extra candidates the tensor filter keeps beyond k+1),
- * "query_block" (queries per internal batch), "pipeline" (1 = default: osml_knn_predict uploads a query matrix of at
- * least two waves of filter work in two blocks, the second under the first block's filter kernel; 0 = one block).
+ * "query_block" (queries per internal batch), "pipeline" (1 = default: osml_knn_predict uploads a query matrix of
+ * 4 MB or more in two blocks, the second under the first block's filter kernel; 0 = one block).
  * Unknown name -> EINVAL. */
 int osml_knn_set_option(osml_knn_index* index, const char* name, double value);
 

@@ -545,9 +545,16 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
     // Pipelined upload: queries are independent, so a large matrix goes up in two blocks.  The first is one full wave of
     // K1 work items (sm_count x 128 queries: every CTA pair sweeps one tile pair, nothing is split); the rest is copied on
     // a second stream once the first block's kernels are queued, i.e. under its K1, instead of in front of everything.
+    // Smaller calls whose upload is worth hiding (4 MB and more) go up in two halves: K1 cuts either half into enough train
+    // segments to fill the machine, so the split costs a few list warm-ups and hides half of the copy.
     const int64_t wave = (int64_t)ix->sm_count * 128;
-    const bool pipelined = ix->opt_pipeline && wave > 0 && q >= 2 * wave && use_tensor_path(ix, wave);
-    const int64_t qa = pipelined ? wave : q;
+    int64_t qa = q;
+    if (ix->opt_pipeline && wave > 0) {
+        if (q >= 2 * wave) qa = wave;
+        else if (q >= 4096 && (size_t)q * ix->d * es >= ((size_t)4 << 20)) qa = (q / 2 + 255) / 256 * 256;
+        if (qa < q && !use_tensor_path(ix, std::min(qa, q - qa))) qa = q;
+    }
+    const bool pipelined = qa < q;
     CUDA_TRY(cudaEventRecord(ix->ev0, ix->stream));
     auto transform_rows = [&](int64_t r0, int64_t r1) -> int {   // raw queries: Centering / Standardization in place
         if (!ix->has_q_transform) return OSML_KNN_OK;
