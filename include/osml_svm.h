@@ -11,6 +11,7 @@
  *                              with _linear_kernel / _polynomial_kernel / _gaussian_kernel (1086-1093) inside
  *   osml_svm_decision_self     the same with the machine's own vectors as queries = the values _update_error_cache
  *                              recomputes after every SMO step, before the labels are subtracted (1101-1105)
+ *   osml_svm_gram              K(x_i, x_j) for all training pairs: the k_ii, k_jj, k_ij of _optimize_ij (1140-1142)
  *   osml_svm_set_multipliers   new multipliers / intercept after an SMO step (the alphas[i], alphas[j], intercept[0]
  *                              assignments of _optimize_ij, 1151-1161)
  *
@@ -58,6 +59,11 @@ int osml_svm_decision(osml_svm_machine* machine, const void* queries, int layout
 
 /* queries = the machine's own vectors; out: n doubles (host) */
 int osml_svm_decision_self(osml_svm_machine* machine, double* out);
+
+/* out[i * n + j] = K(vectors_i, vectors_j) for all pairs of the machine's vectors (n * n doubles, host): the scalar kernel
+ * values _optimize_ij evaluates on single rows (osml/predict.py:1140-1142), once per fit instead of three per attempt.
+ * Values are computed in the data's dtype (single rows: numpy's pairwise order over the features) and widened. */
+int osml_svm_gram(osml_svm_machine* machine, double* out);
 
 /* device pointers: d_queries row-major q x d, d_out q doubles; runs on `stream` (a cudaStream_t; NULL = the handle's
  * own stream, synchronised before returning) */

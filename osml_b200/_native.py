@@ -33,7 +33,7 @@ SYMBOLS = ('osml_knn_create', 'osml_knn_destroy', 'osml_knn_predict', 'osml_knn_
            'osml_knn_abi_version', 'osml_knn_column_transform', 'osml_knn_set_query_transform')
 # every symbol include/osml_svm.h declares
 SVM_SYMBOLS = ('osml_svm_create', 'osml_svm_destroy', 'osml_svm_set_multipliers', 'osml_svm_decision',
-               'osml_svm_decision_self', 'osml_svm_decision_device', 'osml_svm_get_stats')
+               'osml_svm_decision_self', 'osml_svm_decision_device', 'osml_svm_get_stats', 'osml_svm_gram')
 SVM_KERNELS = {'lin': 0, 'poly': 1, 'rbf': 2}
 
 
@@ -84,6 +84,7 @@ def lib():
     cdll.osml_svm_set_multipliers.argtypes = [c_vp, c_vp, c_dbl]
     cdll.osml_svm_decision.argtypes = [c_vp, c_vp, c_int, c_i64, c_vp]
     cdll.osml_svm_decision_self.argtypes = [c_vp, c_vp]
+    cdll.osml_svm_gram.argtypes = [c_vp, c_vp]
     cdll.osml_svm_decision_device.argtypes = [c_vp, c_vp, c_i64, c_vp, c_vp]
     cdll.osml_svm_get_stats.argtypes = [c_vp, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64)]
     for name in SYMBOLS + SVM_SYMBOLS:
@@ -315,6 +316,13 @@ class Machine:
         out = np.empty(self.n, dtype=np.float64)
         check(lib().osml_svm_decision_self(self._handle, out.ctypes.data))
         return out
+
+    def gram(self):
+        """K(v_i, v_j) for all pairs of the machine's vectors, as an (n, n) array of the dtype the reference's kernel
+        function returns for this data (float32 for float32 data, else float64) (osml_svm_gram)."""
+        out = np.empty((self.n, self.n), dtype=np.float64)
+        check(lib().osml_svm_gram(self._handle, out.ctypes.data))
+        return out.astype(np.float32) if self.dtype == np.float32 else out
 
     def decision_device(self, d_queries, q, d_out, stream=None):
         check(lib().osml_svm_decision_device(self._handle, d_queries, int(q), d_out, stream))

@@ -210,6 +210,35 @@ int osml_svm_decision_self(osml_svm_machine* m, double* out) {
     return svm_finish_host_call(m, m->n, out);
 }
 
+int osml_svm_gram(osml_svm_machine* m, double* out) {
+    if (!m || !out) return fail(OSML_KNN_EINVAL, "null argument");
+    if (m->n > 65535) return fail(OSML_KNN_EUNSUPPORTED, "kernel matrix of more than 65535 vectors");
+    DeviceGuard guard(m->device);
+    const size_t bytes = (size_t)m->n * m->n * 8;
+    DeviceBuffer gram;
+    CUDA_TRY(gram.reserve(bytes));
+    cudaError_t e;
+    const int n = (int)m->n, d = (int)m->d;
+    switch (m->dtype) {
+        case OSML_KNN_F32: e = osml::launch_svm_gram<float>(m->kernel, m->vectors.ptr, n, d, m->params, gram.as<double>(), m->stream); break;
+        case OSML_KNN_F64: e = osml::launch_svm_gram<double>(m->kernel, m->vectors.ptr, n, d, m->params, gram.as<double>(), m->stream); break;
+        case OSML_KNN_I8: e = osml::launch_svm_gram<int8_t>(m->kernel, m->vectors.ptr, n, d, m->params, gram.as<double>(), m->stream); break;
+        case OSML_KNN_I16: e = osml::launch_svm_gram<int16_t>(m->kernel, m->vectors.ptr, n, d, m->params, gram.as<double>(), m->stream); break;
+        case OSML_KNN_I32: e = osml::launch_svm_gram<int32_t>(m->kernel, m->vectors.ptr, n, d, m->params, gram.as<double>(), m->stream); break;
+        case OSML_KNN_I64: e = osml::launch_svm_gram<int64_t>(m->kernel, m->vectors.ptr, n, d, m->params, gram.as<double>(), m->stream); break;
+        case OSML_KNN_U8: e = osml::launch_svm_gram<uint8_t>(m->kernel, m->vectors.ptr, n, d, m->params, gram.as<double>(), m->stream); break;
+        case OSML_KNN_U16: e = osml::launch_svm_gram<uint16_t>(m->kernel, m->vectors.ptr, n, d, m->params, gram.as<double>(), m->stream); break;
+        case OSML_KNN_U32: e = osml::launch_svm_gram<uint32_t>(m->kernel, m->vectors.ptr, n, d, m->params, gram.as<double>(), m->stream); break;
+        default: e = osml::launch_svm_gram<uint64_t>(m->kernel, m->vectors.ptr, n, d, m->params, gram.as<double>(), m->stream); break;
+    }
+    m->kernel_launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, gram.ptr, bytes, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    gram.release();
+    if (e != cudaSuccess) return fail(OSML_KNN_ECUDA, cudaGetErrorString(e));
+    return OSML_KNN_OK;
+}
+
 int osml_svm_decision_device(osml_svm_machine* m, const void* d_queries, int64_t q, double* d_out, void* stream_v) {
     if (!m || !d_queries || !d_out) return fail(OSML_KNN_EINVAL, "null argument");
     DeviceGuard guard(m->device);

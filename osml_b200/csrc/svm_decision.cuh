@@ -293,6 +293,42 @@ cudaError_t launch_svm_decision_kind(const void* vectors, const int* active, int
                                                            q_count, p, sm_count, plan, partial, nsplit_out, stream);
 }
 
+// K(V_i, V_j) for all pairs of the machine's own vectors (float64 out, values computed in the data's dtype): the scalar
+// kernel values SMO's step needs (osml/predict.py:1140-1142, evaluated there on (1, d)-shaped rows -- a single row is
+// contiguous along the features, so numpy adds the squared differences with its pairwise tree whatever the matrix order).
+template <typename T, int kKind>
+__global__ void svm_gram_kernel(const T* __restrict__ vectors, int n, int d, SvmParams p, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= n) return;
+    const T* a = vectors + (size_t)i * d;
+    const T* b = vectors + (size_t)j * d;
+    double v;
+    if constexpr (kKind == kSvmGaussian) {
+        typename Elem<T>::Acc acc;
+        if (Elem<T>::kIsFloat) acc = sum_pairwise<T>(a, b, d);
+        else acc = sum_sequential<T>(a, b, d);
+        v = SvmValue<T, kKind>::of(acc, p);
+    } else {
+        T acc = (T)0;
+        for (int f = 0; f < d; ++f) acc = SvmDot<T>::step(acc, a[f], b[f]);
+        v = SvmValue<T, kKind>::of(acc, p);
+    }
+    out[(size_t)i * n + j] = v;
+}
+
+template <typename T>
+cudaError_t launch_svm_gram(int kind, const void* vectors, int n, int d, const SvmParams& p, double* out,
+                            cudaStream_t stream) {
+    const dim3 grid((unsigned)((n + 127) / 128), (unsigned)n);
+    const T* v = static_cast<const T*>(vectors);
+    if (kind == kSvmGaussian) svm_gram_kernel<T, kSvmGaussian><<<grid, 128, 0, stream>>>(v, n, d, p, out);
+    else if constexpr (Elem<T>::kIsFloat) {
+        if (kind == kSvmLinear) svm_gram_kernel<T, kSvmLinear><<<grid, 128, 0, stream>>>(v, n, d, p, out);
+        else svm_gram_kernel<T, kSvmPolynomial><<<grid, 128, 0, stream>>>(v, n, d, p, out);
+    } else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_svm_decision(int kind, const void* vectors, const int* active, int n_active, const double* alphas,
                                 const double* labels, const void* queries, int d, int q_count, bool pairwise,

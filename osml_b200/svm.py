@@ -9,8 +9,10 @@ Same constructor arguments, attributes, bare ``ValueError`` conditions and ``pd.
 GPU is every place the reference evaluates its kernel against ALL rows of a matrix -- ``_raw_predict``
 (osml/predict.py:1095-1099), i.e. ``predict`` / ``fuzzy_predict`` / ``test`` and the error cache SMO recomputes after
 every successful step (``_update_error_cache``, 1101-1105: N decision values over N rows, the fit-time hot spot) -- as
-one call into ``osml_svm_decision`` / ``osml_svm_decision_self`` (include/osml_svm.h).  The SMO bookkeeping itself is
-host control flow as in the reference and draws from ``np.random`` in the same order, so with the same seed it walks
+one call into ``osml_svm_decision`` / ``osml_svm_decision_self`` (include/osml_svm.h) -- and the scalar kernel values
+of SMO's step attempts, taken from a table of all training pairs computed once on the device (``osml_svm_gram``).  The
+SMO bookkeeping itself is host control flow as in the reference (the partner scan tests all candidates of a row in one
+vector pass instead of one by one: same first success) and draws from ``np.random`` in the same order, so with the same seed it walks
 the same path as long as no comparison is decided by the last bits of an error value (the GPU sums in a different
 order: ~1e-16 relative).  There is no CPU fallback for the decision function.
 """
@@ -96,6 +98,9 @@ class BinaryClassificationModel(PredictiveModel):
         return roc, auc
 
 
+GRAM_MAX_ROWS = 8192      # kernel table of the training set: n * n values (512 MB of float64 at the limit)
+
+
 class _Smo:
     """State of one sequential-minimal-optimisation run (osml/predict.py:1118-1236) with the error cache on the GPU."""
 
@@ -111,11 +116,19 @@ class _Smo:
         self.machine = _native.Machine(observations, labels, self.alphas, self.intercept, self.kernel, self.gamma,
                                        self.degree, self.coefficient, device=device)
         self.steps = 0
+        # K(x_i, x_j) for all pairs, computed once on the device (osml_svm_gram) in the data's dtype: the three scalar
+        # kernel values of every step attempt become table look-ups, and the partner search can test all candidates of
+        # a row at once.  Beyond GRAM_MAX_ROWS the table would not fit comfortably; the scalars are then evaluated on
+        # the host like the reference does.
+        self.gram = self.machine.gram() if len(labels) <= GRAM_MAX_ROWS else None
 
     def pair_kernel(self, i, j):
-        """K(x_i, x_j) for two single rows as a numpy scalar of the data's dtype, computed on (1, d)-shaped rows like
-        the reference's calls (osml/predict.py:1120-1121, 1140-1142).  Three scalars per step: host bookkeeping, not
-        the hot path."""
+        """K(x_i, x_j) for two single rows as a numpy scalar of the data's dtype (osml/predict.py:1120-1121, 1140-1142):
+        a look-up in the device-computed table, or -- for training sets too large for the table -- evaluated on
+        (1, d)-shaped rows with the reference's own expressions (three scalars per attempt: bookkeeping, not the hot
+        path)."""
+        if self.gram is not None:
+            return self.gram[i, j]
         a = self.x[i].reshape((1, self.x.shape[1]))
         b = self.x[j].reshape((1, self.x.shape[1]))
         if self.kernel == 'lin':
@@ -174,6 +187,39 @@ class _Smo:
         self.steps += 1
         return True
 
+    def first_partner(self, i, candidates):
+        """Position in ``candidates`` of the first row j for which ``step(i, j)`` would move the multipliers, or -1.
+        A failed attempt has no side effects, so the reference's one-by-one scan (osml/predict.py:1199-1201, 1209-1211)
+        equals: evaluate the three rejection tests of ``step`` for every candidate -- here in one pass of float64 vector
+        arithmetic, element for element the operations ``step`` performs -- and take the first that passes."""
+        c, tol = self.model.c, self.model.tol
+        j = np.asarray(candidates, dtype=np.intp)
+        y_i, a_i, e_i = self.y[i], self.alphas[i], self.errors[i]
+        y_j, a_j, e_j = self.y[j], self.alphas[j], self.errors[j]
+        same = y_j == y_i
+        total, gap = a_i + a_j, a_j - a_i
+        hi = np.minimum(c, np.where(same, total, gap + c))
+        lo = np.maximum(.0, np.where(same, total - c, gap))
+        eta = (self.gram[i, i] + self.gram[j, j] - 2 * self.gram[i, j]).astype(np.float64)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            a_j_new = np.maximum(lo, np.minimum(hi, a_j + y_j * (e_i - e_j) / eta))
+            moves = (hi != lo) & (eta != 0) & ~(np.abs(a_j_new - a_j) < tol)
+        hits = np.flatnonzero(moves)
+        return int(hits[0]) if len(hits) else -1
+
+    def try_partners(self, i, candidates):
+        """``any(step(i, j) for j in candidates)`` with the reference's short-circuit order."""
+        if self.gram is None:
+            return any(self.step(i, j) for j in candidates)
+        while candidates:
+            pos = self.first_partner(i, candidates)
+            if pos < 0:
+                return False
+            if self.step(i, candidates[pos]):           # the scalar step re-checks and performs the update
+                return True
+            candidates = candidates[pos + 1:]            # cannot happen with finite data; keeps the scan faithful
+        return False
+
     def examine(self, i):
         """Picks partners for multiplier i if it violates the KKT conditions (osml/predict.py:1166-1204)."""
         c, tol = self.model.c, self.model.tol
@@ -190,15 +236,13 @@ class _Smo:
             if self.step(i, first):
                 return True
             start = np.random.randint(0, len(unbounded))
-            for j in unbounded[start:] + unbounded[:start]:
-                if j != first and self.step(i, j):
-                    return True
+            if self.try_partners(i, [j for j in unbounded[start:] + unbounded[:start] if j != first]):
+                return True
         at_zero = np.flatnonzero(others & (self.alphas == .0)).tolist()
         if at_zero:
             start = np.random.randint(0, len(at_zero))
-            for j in at_zero[start:] + at_zero[:start]:
-                if self.step(i, j):
-                    return True
+            if self.try_partners(i, at_zero[start:] + at_zero[:start]):
+                return True
         return False
 
     def run(self):

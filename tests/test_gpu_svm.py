@@ -89,6 +89,39 @@ def test_pairwise_feature_sum_of_c_ordered_vectors(dtype, d):
     one.close()
 
 
+@pytest.mark.parametrize('name', ['svm_synth_f32_rbf_forder', 'svm_synth_f64_rbf_corder', 'svm_synth_i8_rbf_wrap',
+                                  'svm_synth_f64_poly', 'svm_synth_f32_poly', 'svm_synth_f64_lin', 'svm_synth_f32_lin'])
+def test_kernel_table_matches_the_pairwise_evaluations_of_the_reference(name):
+    """osml_svm_gram against K(x_i, x_j) evaluated pair by pair on (1, d)-shaped rows, as _optimize_ij does
+    (osml/predict.py:1140-1142): same dtype; rbf to 2.5 ulp of the exact exp of numpy's argument, NaN in the same places
+    (wrapped int8 sums); lin / poly to the accuracy of a d-term dot product in the data's dtype."""
+    g, vectors, args = load_decision_case(name)
+    vectors = vectors[:60]
+    n, d = vectors.shape
+    machine = _native.Machine(vectors, np.ones(n), np.ones(n), 0., **args)
+    got = machine.gram()
+    machine.close()
+    rows = [vectors[i].reshape((1, d)) for i in range(n)]
+    with np.errstate(invalid='ignore'):
+        want = np.array([[so.kernel_values(rows[i], rows[j][0], **args).reshape(-1)[0] for j in range(n)]
+                         for i in range(n)])
+    assert got.dtype == want.dtype and got.shape == (n, n)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    if args['kernel'] == 'rbf':
+        with np.errstate(invalid='ignore'):
+            arg = np.array([[(-args['gamma'] * np.sqrt(np.square(rows[i] - rows[j][0]).sum(axis=1)))[0]
+                             for j in range(n)] for i in range(n)])
+        exact = np.exp(arg.astype(np.float64))
+        ulp = np.spacing(np.abs(exact).astype(want.dtype)).astype(np.float64)
+        assert np.all(np.abs(got.astype(np.float64) - exact)[ok] <= 2.5 * ulp[ok])
+    else:
+        eps = np.finfo(want.dtype).eps
+        mag = np.abs(vectors.astype(np.float64)) @ np.abs(vectors.astype(np.float64)).T + abs(args['poly_coefficient'])
+        bound = 4 * d * eps * (mag if args['kernel'] == 'lin' else args['degree'] * mag ** args['degree'])
+        assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= bound)
+
+
 @pytest.mark.parametrize('name', FITTED_CASES)
 def test_fitted_state_of_the_reference_through_the_model_api(name):
     """The reference's fitted state loaded into the GPU model: decision values, fuzzy memberships, labels, hinge loss and

@@ -116,6 +116,17 @@ class _OracleMachine:
     def decision_self(self):
         return self.decision(self.vectors)
 
+    def gram(self):
+        # pair by pair on (1, d)-shaped rows, exactly as the reference evaluates them (osml/predict.py:1140-1142)
+        n, d = self.vectors.shape
+        rows = [self.vectors[i].reshape((1, d)) for i in range(n)]
+        first = so.kernel_values(rows[0], rows[0][0], **self.args).reshape(-1)[0]
+        out = np.empty((n, n), dtype=np.asarray(first).dtype)
+        for i in range(n):
+            for j in range(n):
+                out[i, j] = so.kernel_values(rows[i], rows[j][0], **self.args).reshape(-1)[0]
+        return out
+
     def close(self):
         pass
 
