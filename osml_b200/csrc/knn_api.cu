@@ -562,7 +562,9 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
         return apply_query_transform(ix, dq, dq, r1 - r0, ix->stream);
     };
     rc = upload_rows(ix, queries, layout, q, ix->d, 0, qa, ix->queries, ix->stream);
-    if (rc == OSML_KNN_OK) rc = transform_rows(0, qa);
+    if (rc != OSML_KNN_OK) return rc;
+    if (pipelined) CUDA_TRY(cudaEventRecord(ix->ev_first, ix->stream));     // the second block's copy starts here
+    rc = transform_rows(0, qa);
     if (rc != OSML_KNN_OK) return rc;
     bool sent = false;
     const std::function<int()> send_rest = [&]() -> int {
@@ -576,7 +578,6 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
         return transform_rows(qa, q);
     };
     if (pipelined) {
-        CUDA_TRY(cudaEventRecord(ix->ev_first, ix->stream));
         ix->before_wait = &send_rest;
         ix->first_block = qa;
     }
