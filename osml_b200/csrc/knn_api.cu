@@ -722,7 +722,7 @@ int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
         const int v = (int)value;
         if (v < OSML_KNN_PATH_AUTO || v > OSML_KNN_PATH_TENSOR) return fail(OSML_KNN_EINVAL, "bad path");
         if (v == OSML_KNN_PATH_TENSOR && !osml::tensor_path_supported(ix->dtype, ix->n, ix->d, ix->k))
-            return fail(OSML_KNN_EUNSUPPORTED, "tensor path needs fp32 data, n >= 256, d <= 8189 and k + 1 + slack <= 64");
+            return fail(OSML_KNN_EUNSUPPORTED, "tensor path needs float32 or float64 data, n >= 256, d <= 8189 and k + 1 + slack <= 64");
         ix->path = v;
         return OSML_KNN_OK;
     }

@@ -92,7 +92,10 @@ struct TcParams {
 // ---------------------------------------------------------------------------------------------------------------------
 // K0: preparation
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void tc_col_partial_sums_kernel(const float* __restrict__ x, int64_t n, int d, int rows_per_block,
+// X = element type of the train / query matrix: float, or double (the filter copy is 16-bit either way; exactness comes
+// from K3, which rescoring in the matrix's own arithmetic)
+template <typename X>
+__global__ void tc_col_partial_sums_kernel(const X* __restrict__ x, int64_t n, int d, int rows_per_block,
                                            double* __restrict__ partial) {
     __shared__ double red[8][33];
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
@@ -147,13 +150,24 @@ __device__ __forceinline__ float tc_value(tc_elem h) {
     return kF16 ? __half2float(__ushort_as_half(h)) : __bfloat162float(__ushort_as_bfloat16(h));
 }
 
+// centred, scaled value as the float that gets rounded to 16 bits, and the same in (all but) exact arithmetic
+__device__ __forceinline__ float tc_centred(float v, float c, float scale) { return __fmul_rn(__fsub_rn(v, c), scale); }
+__device__ __forceinline__ float tc_centred(double v, float c, float scale) {
+    return __double2float_rn((v - (double)c) * (double)scale);
+}
+template <typename X>
+__device__ __forceinline__ double tc_centred_exact(X v, float c, float scale) {
+    return ((double)v - (double)c) * (double)scale;
+}
+
 // max |t - c| over the train set (finite values only): fixes the power-of-two scale of the fp16 filter copy
-__global__ void tc_max_abs_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ center,
+template <typename X>
+__global__ void tc_max_abs_kernel(const X* __restrict__ x, int64_t n, int d, const float* __restrict__ center,
                                   unsigned int* __restrict__ max_bits) {
     const int64_t total = n * d;
     float m = 0.0f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const float a = fabsf(__fsub_rn(x[i], center[i % d]));
+        const float a = fabsf(tc_centred(x[i], center[i % d], 1.0f));
         if (a < INFINITY) m = fmaxf(m, a);
     }
     for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
@@ -162,19 +176,20 @@ __global__ void tc_max_abs_kernel(const float* __restrict__ x, int64_t n, int d,
 
 // Pass A over the train rows (one warp per row): h = 0.5*|t^|^2 of the centred, rounded row, the rounding residual
 // |t^ - (t - c)| and the maxima the completeness bound needs.  h is the sort key of the filter copy.
-template <bool kF16>
-__global__ void tc_train_norms_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ center,
+template <bool kF16, typename X>
+__global__ void tc_train_norms_kernel(const X* __restrict__ x, int64_t n, int d, const float* __restrict__ center,
                                       float scale, float* __restrict__ half_norm, int* __restrict__ iota,
                                       TcPrepStats* stats) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;
-    const float* xr = x + row * d;
+    const X* xr = x + row * d;
     double n2 = 0.0, e2 = 0.0;
     for (int j = lane; j < d; j += 32) {
-        const float v = xr[j], c = center[j];
-        const double hd = (double)tc_value<kF16>(tc_round<kF16>(__fmul_rn(__fsub_rn(v, c), scale)));
-        const double diff = hd - ((double)v - (double)c) * (double)scale;
+        const X v = xr[j];
+        const float c = center[j];
+        const double hd = (double)tc_value<kF16>(tc_round<kF16>(tc_centred(v, c, scale)));
+        const double diff = hd - tc_centred_exact(v, c, scale);
         n2 += hd * hd;
         e2 += diff * diff;
     }
@@ -197,8 +212,8 @@ __global__ void tc_train_norms_kernel(const float* __restrict__ x, int64_t n, in
 // rows nearest to the centre -- the likeliest neighbours of any query -- are scanned first and the per-query
 // thresholds settle early; groups of 8 consecutive rows also get nearly equal h, which keeps the group test tight).
 // Queries (kTrain == false) keep their order and also record |q^|^2 and |q^ - (q - c)|.
-template <bool kTrain, bool kF16>
-__global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t npad, int d, int dp,
+template <bool kTrain, bool kF16, typename X>
+__global__ void tc_prep_rows_kernel(const X* __restrict__ x, int64_t n, int64_t npad, int d, int dp,
                                     const float* __restrict__ center, float scale, const int* __restrict__ perm,
                                     tc_elem* __restrict__ out, double* __restrict__ norm2,
                                     double* __restrict__ err, float* __restrict__ half_norm_sorted,
@@ -213,15 +228,16 @@ __global__ void tc_prep_rows_kernel(const float* __restrict__ x, int64_t n, int6
         if (!kTrain && lane == 0 && norm2) { norm2[row] = 0.0; err[row] = 0.0; }
         return;
     }
-    const float* xr = x + (kTrain ? (int64_t)perm[row] : row) * d;
+    const X* xr = x + (kTrain ? (int64_t)perm[row] : row) * d;
     double n2 = 0.0, e2 = 0.0;
     for (int j = lane; j < d; j += 32) {
-        const float v = xr[j], c = center[j];
-        const tc_elem h = tc_round<kF16>(__fmul_rn(__fsub_rn(v, c), scale));
+        const X v = xr[j];
+        const float c = center[j];
+        const tc_elem h = tc_round<kF16>(tc_centred(v, c, scale));
         o[j] = h;
         if (!kTrain) {
             const double hd = (double)tc_value<kF16>(h);
-            const double diff = hd - ((double)v - (double)c) * (double)scale;
+            const double diff = hd - tc_centred_exact(v, c, scale);
             n2 += hd * hd;
             e2 += diff * diff;
         }
@@ -1155,6 +1171,10 @@ __device__ __forceinline__ float tc_exact_distance(const float* __restrict__ t, 
     }
     return exact_distance<float>(t, q, d, sum_order);
 }
+__device__ __forceinline__ double tc_exact_distance(const double* __restrict__ t, const double* __restrict__ q, int d,
+                                                    int sum_order) {
+    return exact_distance<double>(t, q, d, sum_order);
+}
 
 // One warp per query.  Exact distances are only computed where they can matter: first for the k+1 candidates with the
 // best filter score, whose largest exact distance D0 caps the answer; any other candidate whose score-derived lower
@@ -1167,20 +1187,22 @@ __device__ __forceinline__ unsigned long long tc_score_key(float a, int c) {
     return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)c);   // ties: lowest position
 }
 
-template <int kCand, int kWarps>       // candidates per query the shared-memory lists hold; queries (= warps) per CTA
+// kCand: candidates per query the shared-memory lists hold; kWarps: queries (= warps) per CTA; X: element type of the
+// train / query matrix (float or double) -- distances come out as X
+template <int kCand, int kWarps, typename X>
 __global__ void __launch_bounds__(32 * kWarps)
-knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __restrict__ queries, int d, int sum_order,
+knn_rescore_kernel(const X* __restrict__ train, int64_t n, const X* __restrict__ queries, int d, int sum_order,
                    int64_t q_count, int ksel, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
                    const float* __restrict__ cand_thr, const int* __restrict__ perm, int64_t npad, int nslot,
                    int64_t q_single, int slots_single, int kprime, const double* __restrict__ qnorm2,
-                   const double* __restrict__ qerr, TcBounds bounds, int64_t index_base, float* __restrict__ out_d,
+                   const double* __restrict__ qerr, TcBounds bounds, int64_t index_base, X* __restrict__ out_d,
                    int64_t* __restrict__ out_i, int* __restrict__ flags) {
     static_assert(kCand <= 1024, "the per-lane `taken` mask has 32 bits");
     __shared__ float s_acc[kWarps][kCand];
     __shared__ int s_idx[kWarps][kCand];
-    __shared__ float s_dist[kWarps][kCand];       // exact distances, by position in s_work
+    __shared__ X s_dist[kWarps][kCand];           // exact distances, by position in s_work
     __shared__ short s_work[kWarps][kCand];       // compacted candidate positions: selected, then the rest
-    __shared__ float s_best[kWarps];
+    __shared__ X s_best[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * kWarps + warp;
     if (q >= q_count) return;
@@ -1189,9 +1211,9 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
     const float* ct = cand_thr + (size_t)q * nslot;
     if (q < q_single) nslot = slots_single;           // this query was swept in one item: only its first slots exist
     const int ncand = nslot * kprime;
-    const float* qrow = queries + (size_t)q * d;
+    const X* qrow = queries + (size_t)q * d;
     float* acc = s_acc[warp];
-    float* dist = s_dist[warp];
+    X* dist = s_dist[warp];
     int* idx = s_idx[warp];
     short* work = s_work[warp];
 
@@ -1234,15 +1256,18 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
         if (lane == 0) work[s] = (short)c;
     }
     __syncwarp();
-    float d0 = 0.0f;
+    X d0 = (X)0;
     bool d0_nan = false;
     for (int j = lane; j < nsel; j += 32) {
-        const float dc = tc_exact_distance(train + (size_t)idx[work[j]] * d, qrow, d, sum_order);
+        const X dc = tc_exact_distance(train + (size_t)idx[work[j]] * d, qrow, d, sum_order);
         dist[j] = dc;
-        d0 = fmaxf(d0, dc);
+        d0 = dc > d0 ? dc : d0;
         d0_nan = d0_nan || dc != dc;
     }
-    for (int off = 16; off > 0; off >>= 1) d0 = fmaxf(d0, __shfl_xor_sync(0xffffffffu, d0, off));
+    for (int off = 16; off > 0; off >>= 1) {
+        const X o = __shfl_xor_sync(0xffffffffu, d0, off);
+        d0 = o > d0 ? o : d0;
+    }
     d0_nan = __any_sync(0xffffffffu, d0_nan) || !ok;
     const double cap = d0_nan ? (double)INFINITY : (double)d0 * (1.0 + 9.5367431640625e-07);
     // pass 2: whatever the cap cannot rule out, compacted so that the gathers are spread over the lanes
@@ -1260,7 +1285,7 @@ knn_rescore_kernel(const float* __restrict__ train, int64_t n, const float* __re
     __syncwarp();
     // rank the computed candidates by (distance, index); keys are unique because the slots cover disjoint row sets
     for (int j = lane; j < m; j += 32) {
-        const float dj = dist[j];
+        const X dj = dist[j];
         const int ij = idx[work[j]];
         int rank = 0;
         for (int o = 0; o < m; ++o) rank += key_less(dist[o], idx[work[o]], dj, ij) ? 1 : 0;
@@ -1291,16 +1316,18 @@ __global__ void tc_compact_flags_kernel(const int* __restrict__ flags, int64_t q
     if (q < q_count && flags[q]) list[atomicAdd(count, 1)] = (int)(q + q_offset);
 }
 
-__global__ void tc_gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ list, int count, int d,
-                                      float* __restrict__ dst) {
+template <typename X>
+__global__ void tc_gather_rows_kernel(const X* __restrict__ src, const int* __restrict__ list, int count, int d,
+                                      X* __restrict__ dst) {
     const int r = blockIdx.x;
     if (r >= count) return;
-    const float* s = src + (size_t)list[r] * d;
+    const X* s = src + (size_t)list[r] * d;
     for (int j = threadIdx.x; j < d; j += blockDim.x) dst[(size_t)r * d + j] = s[j];
 }
 
-__global__ void tc_scatter_lists_kernel(const float* __restrict__ src_d, const int64_t* __restrict__ src_i,
-                                        const int* __restrict__ list, int count, int ksel, float* __restrict__ dst_d,
+template <typename X>
+__global__ void tc_scatter_lists_kernel(const X* __restrict__ src_d, const int64_t* __restrict__ src_i,
+                                        const int* __restrict__ list, int count, int ksel, X* __restrict__ dst_d,
                                         int64_t* __restrict__ dst_i) {
     const int r = blockIdx.x;
     if (r >= count) return;
@@ -1397,7 +1424,7 @@ inline int tc_kprime(int k, int slack) {
 }
 
 inline bool tensor_path_supported(int dtype, int64_t n, int64_t d, int k) {
-    if (dtype != 0 /* OSML_KNN_F32 */) return false;
+    if (dtype != 0 /* OSML_KNN_F32 */ && dtype != 1 /* OSML_KNN_F64 */) return false;
     if (n < 256 || d < 1) return false;
     if (d > 8189) return false;                   // 128 K blocks of 64 bf16
     return tc_kprime(k, -1) <= kTcMaxKPrime;
@@ -1449,7 +1476,8 @@ inline int tc_make_map(TensorState& st, CUtensorMap* map, void* base, int64_t ro
         }                                                                                      \
     } while (0)
 
-// one-time K0 over the train set
+// one-time K0 over the train set (X: float or double train matrix)
+template <typename X>
 inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stream, int64_t* launches,
                       std::string* err) {
     const bool f16 = tl.opt_precision == 2 || (tl.opt_precision == 0 && st.want_f16);
@@ -1469,7 +1497,7 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
     const int d = (int)tl.d;
     st.dp = (d + kTcKB - 1) / kTcKB * kTcKB;
     st.npad = (tl.n + kTcBN - 1) / kTcBN * kTcBN;
-    const float* train = static_cast<const float*>(tl.train);
+    const X* train = static_cast<const X*>(tl.train);
     const int rows_per_block = 2048;
     const int nblocks = (int)((tl.n + rows_per_block - 1) / rows_per_block);
     TC_TRY(st.partial.reserve((size_t)nblocks * d * sizeof(double)));
@@ -1508,7 +1536,7 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
             }
             ++*launches;
         }
-        (st.f16 ? tc_train_norms_kernel<true> : tc_train_norms_kernel<false>)<<<(unsigned)((tl.n * 32 + 255) / 256), 256, 0, stream>>>(
+        (st.f16 ? tc_train_norms_kernel<true, X> : tc_train_norms_kernel<false, X>)<<<(unsigned)((tl.n * 32 + 255) / 256), 256, 0, stream>>>(
             train, tl.n, d, st.center.as<float>(), st.scale, keys_in.as<float>(), vals_in.as<int>(),
             st.stats.as<TcPrepStats>());
         size_t temp_bytes = 0;
@@ -1518,7 +1546,7 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
         TC_TRY(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, keys_in.as<float>(), st.half_norm.as<float>(),
                                                vals_in.as<int>(), st.perm.as<int>(), (int)tl.n, 0, 32, stream));
         const int64_t threads = st.npad * 32;
-        (st.f16 ? tc_prep_rows_kernel<true, true> : tc_prep_rows_kernel<true, false>)<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+        (st.f16 ? tc_prep_rows_kernel<true, true, X> : tc_prep_rows_kernel<true, false, X>)<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
             train, tl.n, st.npad, d, st.dp, st.center.as<float>(), st.scale, st.perm.as<int>(),
             st.train_bf16.as<tc_elem>(), nullptr, nullptr, st.half_norm.as<float>(), st.perm.as<int>());
         tc_hblock_kernel<<<(unsigned)((st.npad / 8 + 255) / 256), 256, 0, stream>>>(
@@ -1551,8 +1579,9 @@ inline int tc_prepare(TensorState& st, const TensorLaunch& tl, cudaStream_t stre
 // Filter + rescoring of one block of queries (device, row-major fp32), queued on `stream` without waiting for anything.
 // out_d/out_i: the block's [q][k+1] final lists.  Queries K3 could not prove are appended (as q_offset + local number) to
 // the level's fb_list / fb_count, which the caller reserved and zeroed; tc_resolve_unproven deals with them afterwards.
-inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
-                           float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* launches, std::string* err,
+template <typename X>
+inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_queries, int64_t q,
+                           X* out_d, int64_t* out_i, cudaStream_t stream, int64_t* launches, std::string* err,
                            int level, int64_t q_offset) {
     TensorState::Scratch& sc = st.scratch[level];
     const int d = (int)tl.d;
@@ -1628,7 +1657,7 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const float*
     TC_TRY(sc.flags.reserve((size_t)q * sizeof(int)));
 
     const int64_t threads = qpad * 32;
-    (st.f16 ? tc_prep_rows_kernel<false, true> : tc_prep_rows_kernel<false, false>)<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+    (st.f16 ? tc_prep_rows_kernel<false, true, X> : tc_prep_rows_kernel<false, false, X>)<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
         d_queries, q, qpad, d, st.dp, st.center.as<float>(), st.scale, nullptr, sc.q_bf16.as<tc_elem>(),
         sc.q_norm2.as<double>(), sc.q_err.as<double>(), nullptr, nullptr);
     ++*launches;
@@ -1697,9 +1726,9 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const float*
     b.gamma = (double)(d + 4) * 1.1920928955078125e-07;                      // (D + 4) * 2^-23
     const bool wide_k3 = nslot * kprime > kTcMaxCand;
     const int k3_warps = wide_k3 ? kRescoreWarpsRetry : kRescoreWarps;
-    (wide_k3 ? knn_rescore_kernel<kTcMaxCandRetry, kRescoreWarpsRetry> : knn_rescore_kernel<kTcMaxCand, kRescoreWarps>)
+    (wide_k3 ? knn_rescore_kernel<kTcMaxCandRetry, kRescoreWarpsRetry, X> : knn_rescore_kernel<kTcMaxCand, kRescoreWarps, X>)
         <<<(unsigned)((q + k3_warps - 1) / k3_warps), 32 * k3_warps, 0, stream>>>(
-        static_cast<const float*>(tl.train), tl.n, d_queries, d, tl.sum_order, q, ksel, sc.cand_val.as<float>(),
+        static_cast<const X*>(tl.train), tl.n, d_queries, d, tl.sum_order, q, ksel, sc.cand_val.as<float>(),
         sc.cand_idx.as<int>(), sc.cand_thr.as<float>(), st.perm.as<int>(), st.npad, nslot,
         (int64_t)nq_single * kTcBM * tc_cta_group, halves, kprime, sc.q_norm2.as<double>(), sc.q_err.as<double>(), b, tl.index_base, out_d,
         out_i, sc.flags.as<int>());
@@ -1710,14 +1739,16 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const float*
     return 0;
 }
 
-inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
-                               float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
+template <typename X>
+inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const X* d_queries, int64_t q,
+                               X* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
                                int64_t* launches, std::string* err, const DirectFallback& direct, int level);
 
 // Waits for the blocks queued so far and settles the queries on the level's fb_list (numbers relative to d_queries /
 // out_d / out_i): level 0 re-runs them through a much finer filter pass, level 1 hands them to the exact direct kernel.
-inline int tc_resolve_unproven(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
-                               float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
+template <typename X>
+inline int tc_resolve_unproven(TensorState& st, const TensorLaunch& tl, const X* d_queries, int64_t q,
+                               X* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
                                int64_t* launches, std::string* err, const DirectFallback& direct, int level) {
     TensorState::Scratch& sc = st.scratch[level];
     const int d = (int)tl.d;
@@ -1736,11 +1767,11 @@ inline int tc_resolve_unproven(TensorState& st, const TensorLaunch& tl, const fl
     // many unproven queries mean the bf16 rounding residuals are too large for this data: use fp16 from the next call on
     if (level == 0 && !st.f16 && tl.opt_precision == 0 && q >= 4096 && (int64_t)count * 400 > q) st.want_f16 = true;
     if (count > 0) {
-        TC_TRY(sc.fb_queries.reserve((size_t)count * d * sizeof(float)));
-        TC_TRY(sc.fb_d.reserve((size_t)count * ksel * sizeof(float)));
+        TC_TRY(sc.fb_queries.reserve((size_t)count * d * sizeof(X)));
+        TC_TRY(sc.fb_d.reserve((size_t)count * ksel * sizeof(X)));
         TC_TRY(sc.fb_i.reserve((size_t)count * ksel * sizeof(int64_t)));
-        tc_gather_rows_kernel<<<count, 128, 0, stream>>>(d_queries, sc.fb_list.as<int>(), count, d,
-                                                         sc.fb_queries.as<float>());
+        tc_gather_rows_kernel<X><<<count, 128, 0, stream>>>(d_queries, sc.fb_list.as<int>(), count, d,
+                                                            sc.fb_queries.as<X>());
         ++*launches;
         if (level == 0) {
             // second chance on the filter: the same kernels over the few unproven queries, cut into as many train
@@ -1748,16 +1779,16 @@ inline int tc_resolve_unproven(TensorState& st, const TensorLaunch& tl, const fl
             // many times deeper and the proof almost always goes through.  Whatever still fails goes to K2 from there.
             TensorLaunch retry = tl;
             retry.opt_nseg = 1 << 20;                  // clamped to the maximum
-            rc = tc_neighbours_block(st, retry, sc.fb_queries.as<float>(), count, sc.fb_d.as<float>(),
-                                     sc.fb_i.as<int64_t>(), stream, fallback, launches, err, direct, 1);
+            rc = tc_neighbours_block<X>(st, retry, sc.fb_queries.as<X>(), count, sc.fb_d.as<X>(),
+                                        sc.fb_i.as<int64_t>(), stream, fallback, launches, err, direct, 1);
             st.retry_queries += count;
         } else {
             rc = direct(sc.fb_queries.ptr, count, sc.fb_d.ptr, sc.fb_i.as<int64_t>());
             *fallback += count;
         }
         if (rc) return rc;
-        tc_scatter_lists_kernel<<<count, 64, 0, stream>>>(sc.fb_d.as<float>(), sc.fb_i.as<int64_t>(),
-                                                          sc.fb_list.as<int>(), count, ksel, out_d, out_i);
+        tc_scatter_lists_kernel<X><<<count, 64, 0, stream>>>(sc.fb_d.as<X>(), sc.fb_i.as<int64_t>(),
+                                                             sc.fb_list.as<int>(), count, ksel, out_d, out_i);
         ++*launches;
         TC_TRY(cudaGetLastError());
     }
@@ -1773,20 +1804,22 @@ inline int tc_begin_unproven_list(TensorState& st, int level, int64_t q, cudaStr
 }
 
 // one block, start to finish
-inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const float* d_queries, int64_t q,
-                               float* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
+template <typename X>
+inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const X* d_queries, int64_t q,
+                               X* out_d, int64_t* out_i, cudaStream_t stream, int64_t* fallback,
                                int64_t* launches, std::string* err, const DirectFallback& direct, int level) {
     int rc = tc_begin_unproven_list(st, level, q, stream, err);
     if (rc) return rc;
-    rc = tc_filter_block(st, tl, d_queries, q, out_d, out_i, stream, launches, err, level, 0);
+    rc = tc_filter_block<X>(st, tl, d_queries, q, out_d, out_i, stream, launches, err, level, 0);
     if (rc || tl.debug) return rc;
-    return tc_resolve_unproven(st, tl, d_queries, q, out_d, out_i, stream, fallback, launches, err, direct, level);
+    return tc_resolve_unproven<X>(st, tl, d_queries, q, out_d, out_i, stream, fallback, launches, err, direct, level);
 }
 
-inline int tensor_neighbours(TensorState& st, const TensorLaunch& tl, const void* d_queries, int64_t q, void* out_d,
-                             int64_t* out_i, cudaStream_t stream, int64_t* fallback, int64_t* launches,
-                             std::string* err, const DirectFallback& direct) {
-    int rc = tc_prepare(st, tl, stream, launches, err);
+template <typename X>
+inline int tensor_neighbours_typed(TensorState& st, const TensorLaunch& tl, const void* d_queries, int64_t q, void* out_d,
+                                   int64_t* out_i, cudaStream_t stream, int64_t* fallback, int64_t* launches,
+                                   std::string* err, const DirectFallback& direct) {
+    int rc = tc_prepare<X>(st, tl, stream, launches, err);
     if (rc) return rc;
     st.filter_ms = 0.0;
     st.filter_launches = 0;
@@ -1803,14 +1836,14 @@ inline int tensor_neighbours(TensorState& st, const TensorLaunch& tl, const void
     // pipelined osml_knn_predict uploads the rest of the queries there (and makes `stream` wait for them).
     const int64_t block = 131072;
     const int ksel = tl.k + 1;
-    const float* dq = static_cast<const float*>(d_queries);
-    float* od = static_cast<float*>(out_d);
+    const X* dq = static_cast<const X*>(d_queries);
+    X* od = static_cast<X*>(out_d);
     rc = tc_begin_unproven_list(st, 0, q, stream, err);
     if (rc) return rc;
     st.ev_k1_used = 0;
     int64_t q0 = 0;
     if (tl.first_block > 0 && tl.first_block < q) {
-        rc = tc_filter_block(st, tl, dq, tl.first_block, od, out_i, stream, launches, err, 0, 0);
+        rc = tc_filter_block<X>(st, tl, dq, tl.first_block, od, out_i, stream, launches, err, 0, 0);
         if (rc) return rc;
         q0 = tl.first_block;
     }
@@ -1820,11 +1853,20 @@ inline int tensor_neighbours(TensorState& st, const TensorLaunch& tl, const void
     }
     for (; q0 < q; q0 += block) {
         const int64_t qb = std::min(block, q - q0);
-        rc = tc_filter_block(st, tl, dq + q0 * tl.d, qb, od + q0 * ksel, out_i + q0 * ksel, stream, launches, err, 0, q0);
+        rc = tc_filter_block<X>(st, tl, dq + q0 * tl.d, qb, od + q0 * ksel, out_i + q0 * ksel, stream, launches, err, 0, q0);
         if (rc) return rc;
     }
     if (tl.debug) return 0;
-    return tc_resolve_unproven(st, tl, dq, q, od, out_i, stream, fallback, launches, err, direct, 0);
+    return tc_resolve_unproven<X>(st, tl, dq, q, od, out_i, stream, fallback, launches, err, direct, 0);
+}
+
+// float32 or float64 train / query matrices (tl.dtype); distances come out in the same type
+inline int tensor_neighbours(TensorState& st, const TensorLaunch& tl, const void* d_queries, int64_t q, void* out_d,
+                             int64_t* out_i, cudaStream_t stream, int64_t* fallback, int64_t* launches,
+                             std::string* err, const DirectFallback& direct) {
+    if (tl.dtype == 1 /* OSML_KNN_F64 */)
+        return tensor_neighbours_typed<double>(st, tl, d_queries, q, out_d, out_i, stream, fallback, launches, err, direct);
+    return tensor_neighbours_typed<float>(st, tl, d_queries, q, out_d, out_i, stream, fallback, launches, err, direct);
 }
 
 }  // namespace osml

@@ -375,3 +375,67 @@ def test_small_calls_upload_in_two_halves():
             assert ix.stats()['last_filter_launches'] == (launches if pipeline else 1)
             ix.close()
         assert all(np.array_equal(a, b) for a, b in zip(*out))
+
+
+@pytest.mark.parametrize('n,d,q,k,order', [
+    (20000, 128, 600, 10, 'F'), (5000, 96, 300, 32, 'F'), (3001, 3, 257, 7, 'F'), (10000, 61, 64, 10, 'F'),
+    (6000, 150, 200, 10, 'C'), (2500, 200, 100, 5, 'C'),
+])
+def test_float64_data_takes_the_tensor_path_and_stays_bit_exact(n, d, q, k, order):
+    """pandas' default dtype.  The 16-bit filter copy is built from the float64 matrix, K3 rescoring runs in float64 in
+    numpy's order: distances (float64), indices and labels equal the oracle's bit for bit, as for float32."""
+    rng = np.random.default_rng(n + d + 1)
+    train = np.asarray(rng.standard_normal((n, d)) * 3.0 + 1.5, order=order)
+    test = rng.standard_normal((q, d)) * 3.0 + 1.5
+    labels = rng.integers(0, 10, n)
+    assert train.dtype == np.float64
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    assert dist.dtype == np.float64
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+    assert stats['tensor_queries'] == q
+    if d >= 16:
+        assert stats['fallback_queries'] <= max(2, q // 20), stats
+
+
+def test_float64_regression_ties_and_second_pass_equal_the_direct_kernel():
+    """float64: clustered rows (second filter pass), exact duplicates (direct-kernel fallback), values that differ only
+    below float32 resolution (the filter cannot tell them apart, K3 must), regression output -- against K2."""
+    rng = np.random.default_rng(91)
+    n, d, q, k = 30000, 40, 3000, 9
+    centres = rng.standard_normal((20, d))
+    train = centres[rng.integers(0, 20, n)] + 1e-3 * rng.standard_normal((n, d))
+    train[:2000] = train[2000:4000]                                  # exact duplicates
+    train[4000:6000] = train[6000:8000] + 1e-11                      # distinct only in float64
+    train = np.asfortranarray(train)
+    test = centres[rng.integers(0, 20, q)] + 1e-3 * rng.standard_normal((q, d))
+    labels = rng.standard_normal(n)
+    pred, idx, dist, stats = _run(train, labels, test, k, task='regression', gamma=0.7)
+    assert stats['tensor_queries'] == q and stats['retry_queries'] > 0, stats
+    ix = _native.Index(train, labels, k, 0.7, 1e-8)
+    ix.set_option('path', _native.PATH_DIRECT)
+    d_pred, d_idx, d_dist = ix.predict(test, _native.REGRESSION, return_neighbours=True)
+    ix.close()
+    assert np.array_equal(idx, d_idx) and np.array_equal(dist, d_dist) and np.array_equal(pred, d_pred)
+    sample = rng.choice(q, 48, replace=False)
+    parity.assert_matches_oracle(pred[sample], idx[sample], dist[sample], train, labels, test[sample], k, 0.7,
+                                 'regression')
+
+
+def test_float64_through_the_model_api_with_pipelined_upload():
+    """DataFrame of float64 columns, more than two waves of queries (two-block upload)."""
+    import pandas as pd
+    import osml_b200 as ob
+    rng = np.random.default_rng(92)
+    n, d, q, k = 60000, 24, 2 * 148 * 128 + 777, 7
+    train_df = pd.DataFrame(rng.standard_normal((n, d)))
+    labels = pd.Series(rng.integers(0, 5, n), name='y')
+    query_df = pd.DataFrame(rng.standard_normal((q, d)))
+    model = ob.KNearestNeighborsClassification(k=k)
+    model.path = 'tensor'
+    model.fit(train_df, labels)
+    pred = model.predict(query_df)
+    stats = model._index.stats()
+    assert stats['tensor_queries'] == q and stats['last_filter_launches'] == 2, stats
+    model.path = 'direct'
+    model._drop_index()
+    assert np.array_equal(model.predict(query_df).values, pred.values)
