@@ -106,6 +106,8 @@ struct osml_knn_index {
     int sm_count = 0;
     const std::function<int()>* before_wait = nullptr;   // both set only while a pipelined osml_knn_predict is in flight
     int64_t first_block = 0;
+    int64_t seen_queries = 0;  // since create: auto builds the filter once enough queries have been asked for
+    bool auto_direct = false;  // auto: the filter could not prove most queries of a call, stay on the direct kernel
 
     DeviceBuffer train;        // row-major n x d, original dtype
     DeviceBuffer label_bits;   // int64 per label
@@ -307,8 +309,14 @@ bool use_tensor_path(const osml_knn_index* ix, int64_t q) {
     if (ix->path == OSML_KNN_PATH_DIRECT) return false;
     if (!osml::tensor_path_supported(ix->dtype, ix->n, ix->d, ix->k)) return false;
     if (ix->path == OSML_KNN_PATH_TENSOR) return true;
-    // auto: the filter pays off once the pair count dwarfs its fixed costs
-    return (double)ix->n * (double)q * (double)ix->d >= 2.0e11 && ix->n >= 16384;
+    // auto.  Measured on a fitted index (tools/crossover.py, profiles/r1h_crossover.jsonl): once K0 has run, the filter
+    // beats the direct kernel for every call on the grid, from 20 000 x 32 rows / 32 queries (0.147 vs 0.159 ms) to
+    // 1M x 128 / 2048 queries (0.68 vs 46.9 ms).  K0 itself (two passes over the train set, a sort, the allocations) costs
+    // about what the direct kernel needs for 150 queries, so it is built once that many have been asked for.  Data on
+    // which the completeness proof keeps failing (massive exact ties) would pay for the filter AND the direct kernel:
+    // after such a call auto stays on the direct kernel.
+    if (ix->n < 16384 || ix->auto_direct) return false;
+    return ix->tensor.ready || q + ix->seen_queries >= 128;
 }
 
 // neighbour search into (out_d, out_i): final ascending lists, global indices
@@ -333,6 +341,8 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         ix->stats.kernel_launches += launches;
         if (rc != OSML_KNN_OK) return err.empty() ? rc : fail(rc, err);
         ix->stats.fallback_queries += fallback;
+        ix->seen_queries += q;
+        if (q >= 64 && fallback * 2 > q) ix->auto_direct = true;
         ix->stats.retry_queries += ix->tensor.retry_queries;
         ix->tensor.retry_queries = 0;
         ix->stats.tensor_queries += q;
@@ -340,6 +350,7 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         ix->stats.last_filter_launches = ix->tensor.filter_launches;
         return OSML_KNN_OK;
     }
+    ix->seen_queries += q;
     return launch_direct(ix, d_queries, q, out_d, out_i, stream);
 }
 

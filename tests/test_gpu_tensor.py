@@ -439,3 +439,38 @@ def test_float64_through_the_model_api_with_pipelined_upload():
     model.path = 'direct'
     model._drop_index()
     assert np.array_equal(model.predict(query_df).values, pred.values)
+
+
+def test_auto_path_builds_the_filter_after_128_queries_and_gives_up_on_tie_ridden_data():
+    """path = auto on a fitted index (osml_knn_set_option is never called): the first few queries go to the direct
+    kernel, the filter is built once 128 have been asked for and serves every later call, however small
+    (tools/crossover.py: it wins from 32 queries up); on data whose exact ties defeat the completeness proof for most
+    queries auto returns to the direct kernel after the first such call.  Results are exact either way."""
+    rng = np.random.default_rng(101)
+    n, d, k = 20000, 32, 5
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    labels = rng.integers(0, 4, n)
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    seen = []
+    for q in (50, 100, 10):
+        test = rng.standard_normal((q, d), dtype=np.float32)
+        pred, idx, dist = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+        parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+        seen.append(ix.stats()['tensor_queries'])
+    ix.close()
+    assert seen == [0, 100, 110]
+
+    base = rng.integers(0, 2, (12, d)).astype(np.float32)
+    train = np.asfortranarray(base[rng.integers(0, 12, n)])              # every row repeated ~1700 times
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    test = base[rng.integers(0, 12, 300)]
+    first = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    after_first = ix.stats()
+    second = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    after_second = ix.stats()
+    ix.close()
+    assert after_first['tensor_queries'] == 300 and after_first['fallback_queries'] > 150, after_first
+    assert after_second['tensor_queries'] == 300, after_second                  # the second call never saw the filter
+    assert all(np.array_equal(a, b) for a, b in zip(first, second))
+    parity.assert_matches_oracle(first[0][:40], first[1][:40], first[2][:40], train, labels, test[:40], k, 1,
+                                 'classification')
