@@ -128,3 +128,18 @@ def test_select_deterministic_rule_and_errors():
     assert idx.tolist()[0] == 4 or not np.isnan(d[idx[0]])  # NaN last in ascending order = first in descending
     assert ko.tie_flags(d, 3) == (True, True)
     assert ko.tie_flags(np.array([1., 2., 3., 4., 5., 6.]), 3) == (False, False)
+
+
+def test_single_row_matrices_sum_pairwise_whatever_their_flags_say():
+    """A (1, d) matrix is contiguous along the features in C and in F order, so numpy reduces it with pairwise_sum
+    (the support-vector path meets this: one support vector, and the (1, d)-shaped rows of SMO's kernel calls)."""
+    from osml_b200 import _native
+    rng = np.random.default_rng(5)
+    q = rng.standard_normal(130).astype(np.float32)
+    for order in ('C', 'F'):
+        row = np.asarray(rng.standard_normal((1, 130)).astype(np.float32), order=order)
+        assert ko.sum_order_of(row) == 'pairwise'
+        assert _native.sum_order_of(row) == _native.SUM_PAIRWISE
+        assert np.array_equal(ko.distances(row, q), ko.distances_pairwise(row, q))
+    column = rng.standard_normal((130, 1)).astype(np.float32)
+    assert ko.sum_order_of(column) == 'sequential' and _native.sum_order_of(column) == _native.SUM_SEQUENTIAL
