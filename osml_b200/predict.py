@@ -87,8 +87,13 @@ class ClassificationModel(PredictiveModel):
             raise ValueError
 
     def _evaluate(self, predictions_sr, labels_sr):
-        # accuracy by index label (osml/predict.py:276-278; ``iteritems`` was removed in pandas 2, ``items`` is it)
-        hits = sum(1 for i, p in predictions_sr.items() if p == labels_sr[i])
+        # accuracy by index label (osml/predict.py:276-278; ``iteritems`` was removed in pandas 2, ``items`` is it).
+        # With the same unique index on both series ``labels_sr[i]`` is the element at the same position, so the
+        # reference's per-item loop (a second per 100 000 predictions) is one vector comparison with the same count.
+        if predictions_sr.index.is_unique and predictions_sr.index.equals(labels_sr.index):
+            hits = int(np.count_nonzero(predictions_sr.values == labels_sr.values))
+        else:
+            hits = sum(1 for i, p in predictions_sr.items() if p == labels_sr[i])
         return hits / predictions_sr.count()
 
 

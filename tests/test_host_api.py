@@ -97,3 +97,24 @@ def test_predict_validates_dtypes_against_fit():
         m.predict(X.astype(np.float32))
     with pytest.raises(ValueError):
         m.predict(X.iloc[:0])
+
+
+def test_accuracy_fast_path_equals_the_reference_loop():
+    """ClassificationModel._evaluate compares position by position when both series share a unique index; otherwise it
+    walks the items like the reference (osml/predict.py:276-278).  Same number either way."""
+    rng = np.random.default_rng(3)
+    cls = ob.KNearestNeighborsClassification()
+    cls._label_type = np.dtype(np.int64)
+
+    def loop(p, t):
+        return len([q for i, q in p.items() if q == t[i]]) / p.count()
+
+    for n in (1, 7, 500):
+        p = pd.Series(rng.integers(0, 3, n))
+        t = pd.Series(rng.integers(0, 3, n))
+        assert cls.evaluate(p, t) == loop(p, t)
+        labels = rng.permutation(n) + 10                         # the same non-range index on both
+        p2, t2 = pd.Series(p.values, index=labels), pd.Series(t.values, index=labels)
+        assert cls.evaluate(p2, t2) == loop(p2, t2)
+        t3 = pd.Series(t.values, index=labels[::-1].copy())       # same labels, other order: aligned by label
+        assert cls.evaluate(p2, t3) == loop(p2, t3)
