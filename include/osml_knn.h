@@ -126,6 +126,19 @@ int osml_knn_merge_predict_device(osml_knn_index* index, const int64_t* d_part_i
                                   int parts, int64_t q, int task,
                                   double* d_out_pred, int64_t* d_out_idx, void* d_out_dist, void* stream);
 
+/* Slice-wise exchange of the train-sharded mode ("each GPU merges ... for its ceil(Q/G) query
+ * slice"; the reference keeps the whole matrix in one process, osml/predict.py:770).  pack: this handle's lists for
+ * all q queries ([q][k+1], as osml_knn_neighbours_device wrote them) -> 16-byte records {int64 index, distance bits
+ * (a float32 distance in the low word)} laid out [parts][slice_q][k+1] with slice_q = ceil(q / parts); queries past q
+ * are padded with empty entries.  One all-to-all with equal splits (parts * ... -> every rank receives
+ * [parts][slice_q][k+1]: the partial lists of ITS slice from every rank) feeds merge_predict_packed, which merges the
+ * first q_valid queries of the slice by (distance, index) and aggregates them.  d_out_idx / d_out_dist nullable. */
+int osml_knn_pack_slices_device(osml_knn_index* index, const int64_t* d_idx, const void* d_dist, int64_t q, int parts,
+                                void* d_records, void* stream);
+int osml_knn_merge_predict_packed_device(osml_knn_index* index, const void* d_records, int parts, int64_t slice_q,
+                                         int64_t q_valid, int task, double* d_out_pred, int64_t* d_out_idx,
+                                         void* d_out_dist, void* stream);
+
 /* Options: "path" (enum osml_knn_path), "slack" (extra candidates the tensor filter keeps beyond k+1),
  * "query_block" (queries per internal batch), "pipeline" (1 = default: osml_knn_predict uploads a query matrix of
  * 4 MB or more in two blocks, the second under the first block's filter kernel; 0 = one block).

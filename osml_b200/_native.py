@@ -30,7 +30,8 @@ DTYPE_CODES = {
 SYMBOLS = ('osml_knn_create', 'osml_knn_destroy', 'osml_knn_predict', 'osml_knn_predict_device',
            'osml_knn_neighbours_device', 'osml_knn_merge_predict_device', 'osml_knn_set_option',
            'osml_knn_get_stats', 'osml_knn_reset_stats', 'osml_knn_describe', 'osml_knn_last_error',
-           'osml_knn_abi_version', 'osml_knn_column_transform', 'osml_knn_set_query_transform')
+           'osml_knn_abi_version', 'osml_knn_column_transform', 'osml_knn_set_query_transform',
+           'osml_knn_pack_slices_device', 'osml_knn_merge_predict_packed_device')
 # every symbol include/osml_svm.h declares
 SVM_SYMBOLS = ('osml_svm_create', 'osml_svm_destroy', 'osml_svm_set_multipliers', 'osml_svm_decision',
                'osml_svm_decision_self', 'osml_svm_decision_device', 'osml_svm_get_stats', 'osml_svm_gram')
@@ -68,6 +69,8 @@ def lib():
     cdll.osml_knn_predict_device.argtypes = [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]
     cdll.osml_knn_neighbours_device.argtypes = [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]
     cdll.osml_knn_merge_predict_device.argtypes = [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]
+    cdll.osml_knn_pack_slices_device.argtypes = [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp]
+    cdll.osml_knn_merge_predict_packed_device.argtypes = [c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]
     cdll.osml_knn_set_option.argtypes = [c_vp, ctypes.c_char_p, c_dbl]
     cdll.osml_knn_get_stats.argtypes = [c_vp, ctypes.POINTER(Stats)]
     cdll.osml_knn_reset_stats.argtypes = [c_vp]
@@ -255,6 +258,16 @@ class Index:
                              d_out_dist=None, stream=None):
         check(lib().osml_knn_merge_predict_device(self._handle, d_part_idx, d_part_dist, int(parts), int(q),
                                                   int(task), d_out_pred, d_out_idx, d_out_dist, stream))
+
+    def pack_slices_device(self, d_idx, d_dist, q, parts, d_records, stream=None):
+        """[q][k+1] lists -> 16-byte records [parts][ceil(q / parts)][k+1] (the all-to-all send buffer)."""
+        check(lib().osml_knn_pack_slices_device(self._handle, d_idx, d_dist, int(q), int(parts), d_records, stream))
+
+    def merge_predict_packed_device(self, d_records, parts, slice_q, q_valid, task, d_out_pred, d_out_idx=None,
+                                    d_out_dist=None, stream=None):
+        check(lib().osml_knn_merge_predict_packed_device(self._handle, d_records, int(parts), int(slice_q),
+                                                         int(q_valid), int(task), d_out_pred, d_out_idx, d_out_dist,
+                                                         stream))
 
 
 class Machine:

@@ -17,8 +17,12 @@
 
 namespace osml {
 
-constexpr int kAggMaxK = 128;          // voters per query the kernel supports (k <= 128)
-constexpr int kAggWarpsPerCta = 4;
+constexpr int kAggMaxK = 1025;         // k + 1 entries per query the GPU path supports (k <= 1024)
+constexpr int kAggWarpsPerCta = 4;     // queries (= warps) per CTA while their voters fit in 48 KB of shared memory
+constexpr int kAggBytesPerVoter = 8 + 8 + 8 + 4;
+
+inline int agg_warps_per_cta(int k) { return k <= 384 ? kAggWarpsPerCta : (k <= 768 ? 2 : 1); }
+inline size_t agg_smem_bytes(int k, int warps) { return (size_t)warps * ((size_t)k * kAggBytesPerVoter + 16); }
 
 enum LabelKind { kLabelSigned = 0, kLabelUnsigned = 1, kLabelFloat = 2 };
 
@@ -33,22 +37,27 @@ __device__ __forceinline__ bool label_equal(int64_t a, int64_t b, int kind) {
     return a == b;
 }
 
+// label_is_f32: float32 regression labels.  The reference's `key * value` is then np.float32 * Python float, which numpy 2
+// (NEP 50) evaluates in float32 -- the weight is rounded to float32 first -- `weighted_labels_sum` accumulates in float32
+// and the final division by the (fp64) weight sum rounds the divisor to float32 too (predict.py:788-793).
 template <typename Dist>
 __global__ void __launch_bounds__(32 * kAggWarpsPerCta)
 knn_aggregate_kernel(const Dist* __restrict__ nn_d, const int64_t* __restrict__ nn_i, int64_t q_count, int k,
-                     const int64_t* __restrict__ label_bits, int label_kind, int64_t n_labels,
+                     const int64_t* __restrict__ label_bits, int label_kind, int label_is_f32, int64_t n_labels,
                      double gamma, int gamma_is_f32, double epsilon, int task, double* __restrict__ out_pred) {
-    __shared__ double s_w[kAggWarpsPerCta][kAggMaxK];
-    __shared__ double s_sum[kAggWarpsPerCta][kAggMaxK];
-    __shared__ int64_t s_label[kAggWarpsPerCta][kAggMaxK];
-    __shared__ int s_leader[kAggWarpsPerCta][kAggMaxK];
+    extern __shared__ __align__(16) unsigned char agg_smem[];      // per warp: [k] weights, sums, labels, leaders
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * kAggWarpsPerCta + warp;
+    const int warps = blockDim.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * warps + warp;
     if (q >= q_count) return;
     const int ksel = k + 1;
     const Dist* d = nn_d + q * ksel;
     const int64_t* idx = nn_i + q * ksel;
-    double* w = s_w[warp]; double* gsum = s_sum[warp]; int64_t* lab = s_label[warp]; int* leader = s_leader[warp];
+    unsigned char* mine = agg_smem + (size_t)warp * (((size_t)k * kAggBytesPerVoter + 15) / 16 * 16);
+    double* w = reinterpret_cast<double*>(mine);
+    double* gsum = w + k;
+    int64_t* lab = reinterpret_cast<int64_t*>(gsum + k);
+    int* leader = reinterpret_cast<int*>(lab + k);
 
     const double dn = (double)d[k];
     const double denom = dn + epsilon;                    // predict.py:759  distance_to_normalize_by + self.epsilon
@@ -80,7 +89,15 @@ knn_aggregate_kernel(const Dist* __restrict__ nn_d, const int64_t* __restrict__ 
     __syncwarp();
     if (lane == 0) {
         double result;
-        if (task == 0) {
+        if (task == 0 && label_is_f32) {
+            float wl = 0.0f;
+            double ws = 0.0;
+            for (int v = 0; v < k; ++v) if (leader[v] == v) {
+                wl = __fadd_rn(wl, __fmul_rn((float)label_value(lab[v], label_kind), (float)gsum[v]));
+                ws = __dadd_rn(ws, gsum[v]);
+            }
+            result = (double)__fdiv_rn(wl, (float)ws);
+        } else if (task == 0) {
             double wl = 0.0, ws = 0.0;
             for (int v = 0; v < k; ++v) if (leader[v] == v) {
                 wl = __dadd_rn(wl, __dmul_rn(label_value(lab[v], label_kind), gsum[v]));   // key * value, then +=

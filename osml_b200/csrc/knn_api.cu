@@ -91,6 +91,7 @@ struct osml_knn_index {
     int64_t index_base = 0;
     int64_t n_labels = 0;
     int label_kind = 0;
+    int label_is_f32 = 0;      // float32 regression labels: the reference's weighted sum then runs in float32 (K4)
     int path = OSML_KNN_PATH_AUTO;
     int slack = -1;
     int opt_epi_warps = 0;
@@ -234,7 +235,10 @@ int launch_direct_typed(osml_knn_index* ix, const void* d_queries, int64_t q, vo
     const int ksel = ix->ksel();
     const int n = (int)ix->n, d = (int)ix->d;
     const bool generic = osml::Elem<T>::kIsFloat && ix->sum_order == OSML_KNN_SUM_PAIRWISE && d > 1;
-    const int qgroup = generic ? osml::kDirectQT : osml::kRowQB;
+    // the generic kernel keeps k + 1 (distance, index) entries per thread in shared memory: fewer threads for large k
+    int generic_qt = osml::kDirectQT;
+    while (generic_qt > 8 && (size_t)ksel * generic_qt * (sizeof(Dist) + sizeof(int)) > 200 * 1024) generic_qt /= 2;
+    const int qgroup = generic ? generic_qt : osml::kRowQB;
     const int ctas_q = (int)((q + qgroup - 1) / qgroup);
     // split the train rows until the grid covers the machine a few times over
     const int row_quant = generic ? 64 : osml::kRowThreads;
@@ -259,20 +263,29 @@ int launch_direct_typed(osml_knn_index* ix, const void* d_queries, int64_t q, vo
     }
     dim3 grid((unsigned)ctas_q, (unsigned)nsplit);
     if (generic) {
-        const size_t smem = (size_t)ksel * osml::kDirectQT * (sizeof(Dist) + sizeof(int));
+        const size_t smem = (size_t)ksel * generic_qt * (sizeof(Dist) + sizeof(int));
         auto kern = osml::knn_direct_generic_kernel<T>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, osml::kDirectQT, smem, stream>>>(ix->train.as<T>(), static_cast<const T*>(d_queries), n, d, (int)q,
+        kern<<<grid, generic_qt, smem, stream>>>(ix->train.as<T>(), static_cast<const T*>(d_queries), n, d, (int)q,
                                                       ksel, rows_per_split, ix->index_base, ix->sum_order, part_d,
                                                       part_i);
     } else {
-        const size_t smem = osml::RowSmem<T>::bytes(d, ksel);
-        if (smem > 200 * 1024) return fail(OSML_KNN_EUNSUPPORTED, "row too long for the direct kernel's query tile");
+        // rows too wide for the shared-memory query tile go through it in chunks of d_chunk features (a multiple of 16
+        // elements, so 16-byte row loads stay aligned); the reference has no width limit (predict.py:742)
+        const size_t budget = 200 * 1024;
+        int d_chunk = d;
+        if (osml::RowSmem<T>::bytes(d, ksel) > budget) {
+            const size_t fixed = osml::RowSmem<T>::bytes(0, ksel);
+            if (fixed + 16 * osml::kRowQB * sizeof(T) > budget)
+                return fail(OSML_KNN_EUNSUPPORTED, "k too large for the direct kernel's shared-memory lists");
+            d_chunk = (int)((budget - fixed) / (osml::kRowQB * sizeof(T))) / 16 * 16;
+        }
+        const size_t smem = osml::RowSmem<T>::bytes(d_chunk, ksel);
         // 16-byte row loads need 16-byte aligned rows (the base comes from cudaMalloc)
         const bool vec = ((size_t)d * sizeof(T)) % 16 == 0;
         auto kern = vec ? osml::knn_direct_rows_kernel<T, true> : osml::knn_direct_rows_kernel<T, false>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, osml::kRowThreads, smem, stream>>>(ix->train.as<T>(), static_cast<const T*>(d_queries), n, d,
+        kern<<<grid, osml::kRowThreads, smem, stream>>>(ix->train.as<T>(), static_cast<const T*>(d_queries), n, d, d_chunk,
                                                         (int)q, ksel, rows_per_split, ix->index_base, part_d, part_i);
     }
     ix->stats.kernel_launches++;
@@ -357,16 +370,22 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
 int aggregate(osml_knn_index* ix, const void* nn_d, const int64_t* nn_i, int64_t q, int task, double* d_out_pred,
               cudaStream_t stream) {
     if (task != OSML_KNN_REGRESSION && task != OSML_KNN_CLASSIFICATION) return fail(OSML_KNN_EINVAL, "bad task");
-    const unsigned grid = (unsigned)((q + osml::kAggWarpsPerCta - 1) / osml::kAggWarpsPerCta);
-    const int threads = 32 * osml::kAggWarpsPerCta;
+    const int warps = osml::agg_warps_per_cta(ix->k);
+    const unsigned grid = (unsigned)((q + warps - 1) / warps);
+    const int threads = 32 * warps;
+    const size_t smem = osml::agg_smem_bytes(ix->k, warps);
     if (ix->dist_size() == 4) {
-        osml::knn_aggregate_kernel<float><<<grid, threads, 0, stream>>>(
-            static_cast<const float*>(nn_d), nn_i, q, ix->k, ix->label_bits.as<int64_t>(), ix->label_kind, ix->n_labels,
-            ix->gamma, ix->gamma_is_f32, ix->epsilon, task, d_out_pred);
+        auto kern = osml::knn_aggregate_kernel<float>;
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, stream>>>(
+            static_cast<const float*>(nn_d), nn_i, q, ix->k, ix->label_bits.as<int64_t>(), ix->label_kind,
+            ix->label_is_f32, ix->n_labels, ix->gamma, ix->gamma_is_f32, ix->epsilon, task, d_out_pred);
     } else {
-        osml::knn_aggregate_kernel<double><<<grid, threads, 0, stream>>>(
+        auto kern = osml::knn_aggregate_kernel<double>;
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, stream>>>(
             static_cast<const double*>(nn_d), nn_i, q, ix->k, ix->label_bits.as<int64_t>(), ix->label_kind,
-            ix->n_labels, ix->gamma, ix->gamma_is_f32, ix->epsilon, task, d_out_pred);
+            ix->label_is_f32, ix->n_labels, ix->gamma, ix->gamma_is_f32, ix->epsilon, task, d_out_pred);
     }
     ix->stats.kernel_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -385,7 +404,7 @@ int check_predict_args(const osml_knn_index* ix, int64_t q) {
 
 extern "C" {
 
-int osml_knn_abi_version(void) { return 1003; }
+int osml_knn_abi_version(void) { return 1004; }
 
 const char* osml_knn_last_error(void) { return g_last_error.c_str(); }
 
@@ -405,7 +424,7 @@ int osml_knn_create(osml_knn_index** out, int device, const void* train, int dty
     if (layout != OSML_KNN_ROW_MAJOR && layout != OSML_KNN_COL_MAJOR) return fail(OSML_KNN_EINVAL, "bad layout");
     if (sum_order != OSML_KNN_SUM_PAIRWISE && sum_order != OSML_KNN_SUM_SEQUENTIAL)
         return fail(OSML_KNN_EINVAL, "bad sum_order");
-    if (k + 1 > osml::kAggMaxK) return fail(OSML_KNN_EUNSUPPORTED, "k > 127 is not supported on the GPU path");
+    if (k + 1 > osml::kAggMaxK) return fail(OSML_KNN_EUNSUPPORTED, "k > 1024 is not supported on the GPU path");
     if (n >= 0x7fffffff || d >= (1 << 24)) return fail(OSML_KNN_EUNSUPPORTED, "shard too large (n < 2^31, d < 2^24)");
 
     int count = 0;
@@ -423,6 +442,7 @@ int osml_knn_create(osml_knn_index** out, int device, const void* train, int dty
     std::vector<int64_t> bits;
     if (convert_labels(labels, label_dtype, n_labels, bits, &ix->label_kind))
         return cleanup(fail(OSML_KNN_EUNSUPPORTED, "unsupported label dtype"));
+    ix->label_is_f32 = label_dtype == OSML_KNN_F32 ? 1 : 0;
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -466,6 +486,8 @@ int osml_knn_destroy(osml_knn_index* ix) {
 int osml_knn_neighbours_device(osml_knn_index* ix, const void* d_queries, int64_t q, int64_t* d_out_idx,
                                void* d_out_dist, void* stream) {
     if (!ix || !d_queries || !d_out_idx || !d_out_dist) return fail(OSML_KNN_EINVAL, "null argument");
+    int rc = check_predict_args(ix, q);
+    if (rc != OSML_KNN_OK) return rc;
     DeviceGuard guard(ix->device);
     return neighbours(ix, d_queries, q, d_out_dist, d_out_idx, static_cast<cudaStream_t>(stream));
 }
@@ -573,7 +595,7 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
         return apply_query_transform(ix, dq, dq, r1 - r0, ix->stream);
     };
     rc = upload_rows(ix, queries, layout, q, ix->d, 0, qa, ix->queries, ix->stream);
-    if (rc != OSML_KNN_OK) return rc;
+    if (rc != OSML_KNN_OK) { cudaStreamSynchronize(ix->stream); return rc; }
     if (pipelined) CUDA_TRY(cudaEventRecord(ix->ev_first, ix->stream));     // the second block's copy starts here
     rc = transform_rows(0, qa);
     if (rc != OSML_KNN_OK) return rc;
@@ -597,7 +619,9 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
     ix->before_wait = nullptr;
     ix->first_block = 0;
     if (rc != OSML_KNN_OK) {
-        if (sent) cudaStreamSynchronize(ix->copy_stream);      // the caller's buffer must not be read after we return
+        // the caller's buffer must not be read after we return: uploads may still be in flight on either stream
+        cudaStreamSynchronize(ix->stream);
+        if (sent) cudaStreamSynchronize(ix->copy_stream);
         return rc;
     }
     if (pipelined && !sent) return fail(OSML_KNN_ECUDA, "internal: the second block of queries was never uploaded");
@@ -643,6 +667,60 @@ int osml_knn_merge_predict_device(osml_knn_index* ix, const int64_t* d_part_idx,
     CUDA_TRY(cudaGetLastError());
     rc = aggregate(ix, nn_d, nn_i, q, task, d_out_pred, stream);
     if (rc == OSML_KNN_OK) ix->stats.queries += q;
+    return rc;
+}
+
+int osml_knn_pack_slices_device(osml_knn_index* ix, const int64_t* d_idx, const void* d_dist, int64_t q, int parts,
+                                void* d_records, void* stream_v) {
+    if (!ix || !d_idx || !d_dist || !d_records) return fail(OSML_KNN_EINVAL, "null argument");
+    if (q < 1) return fail(OSML_KNN_EINVAL, "no queries");
+    if (parts < 1 || parts > 64) return fail(OSML_KNN_EINVAL, "parts must be in 1..64");
+    DeviceGuard guard(ix->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int ksel = ix->ksel();
+    const int64_t slice_q = (q + parts - 1) / parts;
+    const int64_t total = (int64_t)parts * slice_q * ksel;
+    const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ix->sm_count * 16);
+    auto* out = static_cast<osml::NeighbourRecord*>(d_records);
+    if (ix->dist_size() == 4)
+        osml::knn_pack_records_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(d_dist), d_idx, q, slice_q,
+                                                                       parts, ksel, out);
+    else
+        osml::knn_pack_records_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(d_dist), d_idx, q,
+                                                                        slice_q, parts, ksel, out);
+    ix->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return OSML_KNN_OK;
+}
+
+int osml_knn_merge_predict_packed_device(osml_knn_index* ix, const void* d_records, int parts, int64_t slice_q,
+                                         int64_t q_valid, int task, double* d_out_pred, int64_t* d_out_idx,
+                                         void* d_out_dist, void* stream_v) {
+    int rc = check_predict_args(ix, q_valid);
+    if (rc != OSML_KNN_OK) return rc;
+    if (!d_records || !d_out_pred) return fail(OSML_KNN_EINVAL, "null argument");
+    if (parts < 1 || parts > 64) return fail(OSML_KNN_EINVAL, "parts must be in 1..64");
+    if (q_valid > slice_q) return fail(OSML_KNN_EINVAL, "more valid queries than the slice holds");
+    DeviceGuard guard(ix->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int ksel = ix->ksel();
+    void* nn_d = d_out_dist;
+    int64_t* nn_i = d_out_idx;
+    if (!nn_d) { CUDA_TRY(ix->nn_d.reserve((size_t)q_valid * ksel * ix->dist_size())); nn_d = ix->nn_d.ptr; }
+    if (!nn_i) { CUDA_TRY(ix->nn_i.reserve((size_t)q_valid * ksel * 8)); nn_i = ix->nn_i.as<int64_t>(); }
+    const int threads = 128;
+    const unsigned grid = (unsigned)((q_valid + threads - 1) / threads);
+    const auto* in = static_cast<const osml::NeighbourRecord*>(d_records);
+    if (ix->dist_size() == 4)
+        osml::knn_merge_records_kernel<float><<<grid, threads, 0, stream>>>(in, parts, slice_q, q_valid, ksel,
+                                                                            static_cast<float*>(nn_d), nn_i);
+    else
+        osml::knn_merge_records_kernel<double><<<grid, threads, 0, stream>>>(in, parts, slice_q, q_valid, ksel,
+                                                                             static_cast<double*>(nn_d), nn_i);
+    ix->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    rc = aggregate(ix, nn_d, nn_i, q_valid, task, d_out_pred, stream);
+    if (rc == OSML_KNN_OK) ix->stats.queries += q_valid;
     return rc;
 }
 

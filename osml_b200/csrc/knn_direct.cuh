@@ -15,23 +15,23 @@ constexpr int kDirectQT = 128;   // queries (= threads) per CTA
 
 template <typename Dist>
 struct TopList {
-    // shared-memory list of one thread: slot e of thread t lives at d[e * kDirectQT + t]
-    Dist* d; int* i; int ksel;
-    __device__ __forceinline__ void init(Dist* dbase, int* ibase, int ksel_, int tid) {
-        d = dbase + tid; i = ibase + tid; ksel = ksel_;
-        for (int e = 0; e < ksel; ++e) { d[e * kDirectQT] = nan_of<Dist>(); i[e * kDirectQT] = kIdxSentinel; }
+    // shared-memory list of one thread: slot e of thread t lives at d[e * stride + t] (stride = threads per CTA)
+    Dist* d; int* i; int ksel; int stride;
+    __device__ __forceinline__ void init(Dist* dbase, int* ibase, int ksel_, int tid, int stride_) {
+        d = dbase + tid; i = ibase + tid; ksel = ksel_; stride = stride_;
+        for (int e = 0; e < ksel; ++e) { d[e * stride] = nan_of<Dist>(); i[e * stride] = kIdxSentinel; }
     }
-    __device__ __forceinline__ Dist worst_d() const { return d[(ksel - 1) * kDirectQT]; }
-    __device__ __forceinline__ int worst_i() const { return i[(ksel - 1) * kDirectQT]; }
+    __device__ __forceinline__ Dist worst_d() const { return d[(ksel - 1) * stride]; }
+    __device__ __forceinline__ int worst_i() const { return i[(ksel - 1) * stride]; }
     // precondition: key_less(dc, ic, worst)
     __device__ __forceinline__ void insert(Dist dc, int ic) {
         int pos = ksel - 1;
-        while (pos > 0 && key_less(dc, ic, d[(pos - 1) * kDirectQT], i[(pos - 1) * kDirectQT])) {
-            d[pos * kDirectQT] = d[(pos - 1) * kDirectQT];
-            i[pos * kDirectQT] = i[(pos - 1) * kDirectQT];
+        while (pos > 0 && key_less(dc, ic, d[(pos - 1) * stride], i[(pos - 1) * stride])) {
+            d[pos * stride] = d[(pos - 1) * stride];
+            i[pos * stride] = i[(pos - 1) * stride];
             --pos;
         }
-        d[pos * kDirectQT] = dc; i[pos * kDirectQT] = ic;
+        d[pos * stride] = dc; i[pos * stride] = ic;
     }
 };
 
@@ -66,16 +66,16 @@ struct RowSmem {
 
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(kRowThreads)
-knn_direct_rows_kernel(const T* __restrict__ train, const T* __restrict__ queries, int n, int d, int q_count, int ksel,
-                       int rows_per_split, int64_t index_base, typename Elem<T>::Dist* __restrict__ part_d,
+knn_direct_rows_kernel(const T* __restrict__ train, const T* __restrict__ queries, int n, int d, int d_chunk, int q_count,
+                       int ksel, int rows_per_split, int64_t index_base, typename Elem<T>::Dist* __restrict__ part_d,
                        int64_t* __restrict__ part_i) {
     using E = Elem<T>;
     using Acc = typename E::Acc;
     using Dist = typename E::Dist;
     constexpr int kVecElems = kVec ? (int)(16 / sizeof(T)) : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* q_s = reinterpret_cast<T*>(smem_raw);                                              // [d][kRowQB]
-    const size_t q_bytes = ((size_t)d * kRowQB * sizeof(T) + 15) / 16 * 16;
+    T* q_s = reinterpret_cast<T*>(smem_raw);                                              // [d_chunk][kRowQB]
+    const size_t q_bytes = ((size_t)d_chunk * kRowQB * sizeof(T) + 15) / 16 * 16;
     Dist* buf_d = reinterpret_cast<Dist*>(smem_raw + q_bytes);                            // [kRowQB][kRowThreads]
     Dist* list_d = buf_d + kRowQB * kRowThreads;                                          // [kRowQB][ksel]
     int* buf_i = reinterpret_cast<int*>(list_d + kRowQB * ksel);                          // [kRowQB][kRowThreads]
@@ -89,36 +89,53 @@ knn_direct_rows_kernel(const T* __restrict__ train, const T* __restrict__ querie
     const int n_begin = min(n, split * rows_per_split);
     const int n_end = min(n, n_begin + rows_per_split);
 
-    for (int e = tid; e < d * kRowQB; e += kRowThreads) {
-        const int j = e / kRowQB, qi = e % kRowQB;
-        q_s[e] = (q0 + qi < q_count) ? queries[(size_t)(q0 + qi) * d + j] : (T)0;
-    }
+    // The query tile holds d_chunk features of the 8 queries: the whole row (d_chunk == d, loaded once) or, for rows
+    // too wide for shared memory, one chunk at a time (reloaded per batch of rows; every thread keeps its 8 running
+    // sums across the chunks, so the summation order is unchanged).
+    const bool chunked = d_chunk < d;
+    auto load_queries = [&](int c0, int cw) {
+        for (int e = tid; e < cw * kRowQB; e += kRowThreads) {
+            const int j = e / kRowQB, qi = e % kRowQB;
+            q_s[e] = (q0 + qi < q_count) ? queries[(size_t)(q0 + qi) * d + c0 + j] : (T)0;
+        }
+    };
+    if (!chunked) load_queries(0, d);
     for (int e = lane; e < ksel; e += 32) { list_d[warp * ksel + e] = nan_of<Dist>(); list_i[warp * ksel + e] = kIdxSentinel; }
     if (tid < kRowQB) { s_cnt[tid] = 0; s_thr[tid] = E::threshold(nan_of<Dist>()); }
     __syncthreads();
 
     for (int row0 = n_begin; row0 < n_end; row0 += kRowThreads) {
         const int row = row0 + tid;
-        if (row < n_end) {
-            const T* __restrict__ trow = train + (size_t)row * d;
-            Acc acc[kRowQB];
+        Acc acc[kRowQB];
 #pragma unroll
-            for (int qi = 0; qi < kRowQB; ++qi) acc[qi] = (Acc)0;
-            for (int j0 = 0; j0 < d; j0 += kVecElems) {
-                T tv[kVecElems];
-                if (kVec) {
-                    const int4 raw = __ldg(reinterpret_cast<const int4*>(trow + j0));
-                    *reinterpret_cast<int4*>(tv) = raw;
-                } else {
-                    tv[0] = trow[j0];
-                }
+        for (int qi = 0; qi < kRowQB; ++qi) acc[qi] = (Acc)0;
+        for (int c0 = 0; c0 < d; c0 += d_chunk) {
+            const int cw = min(d_chunk, d - c0);
+            if (chunked) {
+                __syncthreads();                       // everyone is done with the previous chunk
+                load_queries(c0, cw);
+                __syncthreads();
+            }
+            if (row < n_end) {
+                const T* __restrict__ trow = train + (size_t)row * d + c0;
+                for (int j0 = 0; j0 < cw; j0 += kVecElems) {
+                    T tv[kVecElems];
+                    if (kVec) {
+                        const int4 raw = __ldg(reinterpret_cast<const int4*>(trow + j0));
+                        *reinterpret_cast<int4*>(tv) = raw;
+                    } else {
+                        tv[0] = trow[j0];
+                    }
 #pragma unroll
-                for (int jj = 0; jj < kVecElems; ++jj) {
-                    const T* qv = q_s + (size_t)(j0 + jj) * kRowQB;
+                    for (int jj = 0; jj < kVecElems; ++jj) {
+                        const T* qv = q_s + (size_t)(j0 + jj) * kRowQB;
 #pragma unroll
-                    for (int qi = 0; qi < kRowQB; ++qi) acc[qi] = E::add(acc[qi], E::sq_diff(tv[jj], qv[qi]));
+                        for (int qi = 0; qi < kRowQB; ++qi) acc[qi] = E::add(acc[qi], E::sq_diff(tv[jj], qv[qi]));
+                    }
                 }
             }
+        }
+        if (row < n_end) {
 #pragma unroll
             for (int qi = 0; qi < kRowQB; ++qi) {
                 if (E::may_beat(acc[qi], s_thr[qi])) {
@@ -161,7 +178,8 @@ knn_direct_rows_kernel(const T* __restrict__ train, const T* __restrict__ querie
 }
 
 // any summation order, no tiling: one thread per query, rows streamed from L2.  Only used for the pairwise (C-ordered)
-// float case, which pandas >= 3 never produces (DataFrame.values is F-ordered there).
+// float case, which pandas >= 3 never produces (DataFrame.values is F-ordered there).  blockDim.x = queries per CTA:
+// kDirectQT, fewer when k + 1 entries per thread would not fit in shared memory otherwise.
 template <typename T>
 __global__ void __launch_bounds__(kDirectQT)
 knn_direct_generic_kernel(const T* __restrict__ train, const T* __restrict__ queries, int n, int d, int q_count,
@@ -171,14 +189,15 @@ knn_direct_generic_kernel(const T* __restrict__ train, const T* __restrict__ que
     using Dist = typename E::Dist;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Dist* list_d = reinterpret_cast<Dist*>(smem_raw);
-    int* list_i = reinterpret_cast<int*>(list_d + (size_t)ksel * kDirectQT);
+    const int qt = blockDim.x;
+    int* list_i = reinterpret_cast<int*>(list_d + (size_t)ksel * qt);
     const int tid = threadIdx.x;
-    const int qq = blockIdx.x * kDirectQT + tid;
+    const int qq = blockIdx.x * qt + tid;
     const int split = blockIdx.y, nsplit = gridDim.y;
     const int n_begin = min(n, split * rows_per_split);
     const int n_end = min(n, n_begin + rows_per_split);
     TopList<Dist> list;
-    list.init(list_d, list_i, ksel, tid);
+    list.init(list_d, list_i, ksel, tid, qt);
     if (qq >= q_count) return;
     Dist wd = nan_of<Dist>();
     int wi = kIdxSentinel;
@@ -192,8 +211,8 @@ knn_direct_generic_kernel(const T* __restrict__ train, const T* __restrict__ que
     }
     const size_t base = ((size_t)qq * nsplit + split) * ksel;
     for (int e = 0; e < ksel; ++e) {
-        const int li = list.i[e * kDirectQT];
-        part_d[base + e] = list.d[e * kDirectQT];
+        const int li = list.i[e * qt];
+        part_d[base + e] = list.d[e * qt];
         part_i[base + e] = li == kIdxSentinel ? kIdxSentinel64 : index_base + li;
     }
 }
@@ -207,7 +226,7 @@ __global__ void knn_merge_lists_kernel(const Dist* __restrict__ in_d, const int6
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= q_count) return;
     constexpr int kMaxParts = 64;
-    unsigned char head[kMaxParts];
+    unsigned short head[kMaxParts];
     for (int p = 0; p < parts; ++p) head[p] = 0;
     const int64_t qbase = q * q_stride;
     for (int e = 0; e < ksel; ++e) {
@@ -220,6 +239,62 @@ __global__ void knn_merge_lists_kernel(const Dist* __restrict__ in_d, const int6
             const Dist cd = in_d[at];
             const int64_t ci = in_i[at];
             if (best < 0 || key_less(cd, ci, bd, bi)) { best = p; bd = cd; bi = ci; }
+        }
+        if (best >= 0) ++head[best];
+        out_d[q * ksel + e] = bd;
+        out_i[q * ksel + e] = bi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Train-sharded exchange: every GPU holds exact partial lists for ALL queries over its own rows,
+// but only has to merge the queries of its own slice.  The lists travel as 16-byte records {int64 index, distance bits}
+// (a float32 distance in the low word), laid out [destination rank][query of its slice][entry], so that ONE
+// all-to-all with equal splits hands every rank the G partial lists of its ceil(Q / G) queries.
+// ---------------------------------------------------------------------------------------------------------------------
+struct alignas(16) NeighbourRecord { int64_t index; unsigned long long dist_bits; };
+
+template <typename Dist> __device__ __forceinline__ unsigned long long dist_to_bits(Dist d);
+template <> __device__ __forceinline__ unsigned long long dist_to_bits<float>(float d) { return (unsigned long long)__float_as_uint(d); }
+template <> __device__ __forceinline__ unsigned long long dist_to_bits<double>(double d) { return (unsigned long long)__double_as_longlong(d); }
+template <typename Dist> __device__ __forceinline__ Dist dist_from_bits(unsigned long long b);
+template <> __device__ __forceinline__ float dist_from_bits<float>(unsigned long long b) { return __uint_as_float((uint32_t)b); }
+template <> __device__ __forceinline__ double dist_from_bits<double>(unsigned long long b) { return __longlong_as_double((long long)b); }
+
+// lists [q][ksel] -> records [parts][slice_q][ksel]; queries past q (padding of the last slice) get empty entries
+template <typename Dist>
+__global__ void knn_pack_records_kernel(const Dist* __restrict__ in_d, const int64_t* __restrict__ in_i, int64_t q_count,
+                                        int64_t slice_q, int parts, int ksel, NeighbourRecord* __restrict__ out) {
+    const int64_t total = (int64_t)parts * slice_q * ksel;
+    for (int64_t at = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; at < total; at += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = at / ksel;                  // [parts][slice_q] flattened == the query number
+        NeighbourRecord r;
+        if (q < q_count) { r.index = in_i[at]; r.dist_bits = dist_to_bits<Dist>(in_d[at]); }
+        else { r.index = kIdxSentinel64; r.dist_bits = dist_to_bits<Dist>(nan_of<Dist>()); }
+        out[at] = r;
+    }
+}
+
+// records [parts][slice_q][ksel] (part p = the list rank p computed over its rows) -> merged ascending lists of the
+// first q_count queries of the slice, by (distance, index).  One thread per query.
+template <typename Dist>
+__global__ void knn_merge_records_kernel(const NeighbourRecord* __restrict__ in, int parts, int64_t slice_q,
+                                         int64_t q_count, int ksel, Dist* __restrict__ out_d,
+                                         int64_t* __restrict__ out_i) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= q_count) return;
+    constexpr int kMaxParts = 64;
+    unsigned short head[kMaxParts];
+    for (int p = 0; p < parts; ++p) head[p] = 0;
+    for (int e = 0; e < ksel; ++e) {
+        int best = -1;
+        Dist bd = nan_of<Dist>();
+        int64_t bi = kIdxSentinel64;
+        for (int p = 0; p < parts; ++p) {
+            if (head[p] >= ksel) continue;
+            const NeighbourRecord r = in[((int64_t)p * slice_q + q) * ksel + head[p]];
+            const Dist cd = dist_from_bits<Dist>(r.dist_bits);
+            if (best < 0 || key_less(cd, r.index, bd, bi)) { best = p; bd = cd; bi = r.index; }
         }
         if (best >= 0) ++head[best];
         out_d[q * ksel + e] = bd;

@@ -1006,7 +1006,8 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 const int ntiles = (p.tiles_total - seg + nsg - 1) / nsg;
                 // seed the threshold with what earlier segments of the same query already proved: their K'-th best
                 // bounds this query's answer from below, so rows scoring under it cannot matter here either.  The slots
-                // are written by other CTAs of this launch; an unfinished one still reads -inf (memset before launch).
+                // are written by other CTAs of this launch; an unfinished one still reads the NaN bits of the memset in
+                // front of the launch, which fmaxf ignores.
                 const size_t q = (size_t)qt * kTcBM + m;
                 float seed = -INFINITY;
                 for (int s2 = 0; s2 < seg; ++s2)

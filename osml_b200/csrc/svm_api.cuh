@@ -72,7 +72,7 @@ cudaError_t svm_launch_typed(osml_svm_machine* m, const void* d_queries, int q, 
 int svm_decide(osml_svm_machine* m, const void* d_queries, int64_t q, double* d_out, cudaStream_t stream) {
     if (q < 1) return fail(OSML_KNN_EINVAL, "no queries");
     if (q > 0x7fffffff / 16) return fail(OSML_KNN_EUNSUPPORTED, "more than 2^27 queries in one call");
-    const int splits = osml::svm_max_splits((int)q, m->n_active, m->sm_count);
+    const int splits = osml::svm_partial_splits((int)q, m->n_active, m->sm_count);
     CUDA_TRY(m->partial.reserve((size_t)splits * q * 8));
     int nsplit = 1;
     CUDA_TRY(cudaEventRecord(m->ev0, stream));

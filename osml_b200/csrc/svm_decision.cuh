@@ -249,7 +249,7 @@ __global__ void svm_finish_kernel(const double* __restrict__ partial, int nsplit
     out[q] = __dadd_rn(intercept, s);          // predictions[i] = float(intercept); predictions[i] += np.sum(...)
 }
 
-inline int svm_max_splits(int q_count, int n_active, int sm_count, int qb = 4) {
+inline int svm_max_splits(int q_count, int n_active, int sm_count, int qb) {
     const int qtiles = (q_count + qb - 1) / qb;
     // enough CTAs for two waves when the query count alone does not give them; a split is at least one batch of rows
     int nsplit = 1;
@@ -257,7 +257,13 @@ inline int svm_max_splits(int q_count, int n_active, int sm_count, int qb = 4) {
     return std::max(1, std::min(nsplit, 65535));
 }
 
-// partial must hold svm_max_splits(q_count, n_active, sm_count) * q_count doubles
+// The row splits a launch may use whatever query group (4 or 8 queries per CTA) its instance picks: fewer queries per
+// CTA -> more query tiles -> fewer splits, so the larger group bounds both.
+inline int svm_partial_splits(int q_count, int n_active, int sm_count) {
+    return std::max(svm_max_splits(q_count, n_active, sm_count, 4), svm_max_splits(q_count, n_active, sm_count, 8));
+}
+
+// partial must hold svm_partial_splits(q_count, n_active, sm_count) * q_count doubles
 template <typename T, int kKind, bool kPairwise, int kQB>
 cudaError_t launch_svm_decision_qb(const void* vectors, const int* active, int n_active, const double* alphas,
                                    const double* labels, const void* queries, int d, int q_count, const SvmParams& p,

@@ -8,9 +8,12 @@ The reference has no multi-device story; the two modes b
   every rank returns the full Series like the reference would).  No data-path collective.
 * **train-sharded** (`TrainShardedIndex`): rank r holds train rows [r * ceil(N / G), ...) plus the full label vector.
   Every rank runs the neighbour search over all queries on its rows (exact distances in the oracle's arithmetic,
-  global row indices), the partial (k+1)-lists are exchanged with ONE all-gather over NCCL / NVLink, and each rank
-  merges the G lists per query by (distance, index) and aggregates.  The merge is exact, so the result is
-  bit-identical to the single-GPU one.
+  global row indices).  The partial (k+1)-lists are packed as 16-byte records, one block per destination rank, and
+  ONE all-to-all over NCCL / NVLink hands rank r the G partial lists of ITS slice of ceil(Q / G) queries only; it
+  merges them by (distance, index), aggregates, and a final all-gather of ceil(Q / G) doubles per rank gives every
+  rank all Q predictions.  The merge is exact, so the result is bit-identical to the single-GPU one.
+  (`exchange='allgather'` keeps the first round's form -- every rank receives and merges all Q lists -- as the
+  independent check `bench.py` and the tests compare against.)
 
 The arithmetic is always the CUDA path (`NativeBackend`); the `backend_factory` argument exists so the collective and
 slicing logic can be exercised on CPU with gloo in tests/test_dist_gloo.py (with a test double, never in production).
@@ -52,13 +55,21 @@ class NativeBackend:
         self.dist_dtype = torch.float32 if self.index.dist_dtype == np.float32 else torch.float64
 
     def neighbours(self, queries):
-        """queries: host (Q, D) array, or a contiguous CUDA tensor already on this device."""
+        """queries: host (Q, D) array, or a contiguous CUDA tensor already on this device; dtype and width must be
+        the index's (the C entry points take raw pointers and cannot check)."""
         torch = self.torch
         q = queries.shape[0]
+        if queries.ndim != 2 or queries.shape[1] != self.index.d:
+            raise ValueError
         with torch.cuda.device(self.device):
             if isinstance(queries, torch.Tensor):
+                if (queries.dtype != getattr(torch, np.dtype(self.index.dtype).name) or not queries.is_contiguous()
+                        or queries.device != self.device):
+                    raise ValueError
                 d_q = queries
             else:
+                if queries.dtype != self.index.dtype:
+                    raise ValueError
                 d_q = torch.from_numpy(np.ascontiguousarray(queries)).to(self.device)
             idx = torch.empty((q, self.k + 1), dtype=torch.int64, device=self.device)
             dist = torch.empty((q, self.k + 1), dtype=self.dist_dtype, device=self.device)
@@ -76,6 +87,31 @@ class NativeBackend:
                                             pred.data_ptr(), None, None, stream)
             return pred if keep_on_device else pred.cpu().numpy()
 
+    def pack_slices(self, idx, dist, parts):
+        """Lists of all Q queries -> the all-to-all send buffer: int64 tensor [parts, ceil(Q / parts), k+1, 2]
+        (16-byte records: global index, distance bits)."""
+        torch = self.torch
+        q, ksel = idx.shape
+        slice_q = -(-q // parts)
+        with torch.cuda.device(self.device):
+            records = torch.empty((parts, slice_q, ksel, 2), dtype=torch.int64, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.index.pack_slices_device(idx.data_ptr(), dist.data_ptr(), q, parts, records.data_ptr(), stream)
+        return records
+
+    def merge_predict_packed(self, records, q_valid, task):
+        """records [parts, slice_q, k+1, 2] = every rank's partial lists of this rank's slice -> fp64 predictions of
+        the slice as a tensor of slice_q entries (the first q_valid are meaningful)."""
+        torch = self.torch
+        parts, slice_q = records.shape[0], records.shape[1]
+        with torch.cuda.device(self.device):
+            pred = torch.zeros(slice_q, dtype=torch.float64, device=self.device)
+            if q_valid > 0:
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+                self.index.merge_predict_packed_device(records.data_ptr(), parts, slice_q, q_valid, task,
+                                                       pred.data_ptr(), None, None, stream)
+        return pred
+
     def close(self):
         self.index.close()
 
@@ -84,7 +120,7 @@ class TrainShardedIndex:
     """Train rows sharded across the ranks of `group`; predictions bit-identical to the unsharded index."""
 
     def __init__(self, train, labels, k, rbf_gamma=1, epsilon=1e-8, device=None, group=None, backend_factory=None,
-                 query_block=131072, path='auto', shard_of=None):
+                 query_block=131072, path='auto', shard_of=None, exchange='alltoall'):
         """`train` is the whole (N, D) matrix (every rank slices its block), or -- with shard_of=(lo, N) -- this rank's
         rows [lo, lo + len(train)) of a matrix of N rows that no single process has to hold.  `labels` always has N
         entries."""
@@ -114,6 +150,9 @@ class TrainShardedIndex:
         self.backend = factory(shard, np.ascontiguousarray(labels), k, rbf_gamma, epsilon, lo, device, sum_order,
                                path)
         self.query_block = int(query_block)
+        if exchange not in ('alltoall', 'allgather'):
+            raise ValueError
+        self.exchange = exchange
 
     def predict(self, queries, task, keep_on_device=False):
         """queries: the same (Q, D) matrix on every rank (host array, or a CUDA tensor on this rank's device).
@@ -128,26 +167,48 @@ class TrainShardedIndex:
         for q0 in range(0, queries.shape[0], self.query_block):
             block = queries[q0:q0 + self.query_block]
             idx, dist_ = self.backend.neighbours(block)
-            if self.world > 1:
-                dist = _dist()
-                import torch
-                qb, ksel = idx.shape
-                all_idx = torch.empty((self.world * qb, ksel), dtype=idx.dtype, device=idx.device)
-                all_dist = torch.empty((self.world * qb, ksel), dtype=dist_.dtype, device=dist_.device)
-                dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=self.group)
-                dist.all_gather_into_tensor(all_dist, dist_.contiguous(), group=self.group)
-                all_idx = all_idx.view(self.world, qb, ksel)          # [part][q][k+1], the C ABI's merge layout
-                all_dist = all_dist.view(self.world, qb, ksel)
+            if self.world > 1 and self.exchange == 'alltoall':
+                pred = self._exchange_slices(idx, dist_, task)
+            elif self.world > 1:
+                pred = self._exchange_all(idx, dist_, task)
             else:
-                all_idx, all_dist = idx[None], dist_[None]
+                pred = self.backend.merge_predict(idx[None], dist_[None], task, keep_on_device=True)
             if keep_on_device:
-                outs.append(self.backend.merge_predict(all_idx, all_dist, task, keep_on_device=True))
+                outs.append(pred)
             else:
-                out[q0:q0 + block.shape[0]] = self.backend.merge_predict(all_idx, all_dist, task)
+                out[q0:q0 + block.shape[0]] = pred.cpu().numpy()
         if keep_on_device:
             import torch
             return outs[0] if len(outs) == 1 else torch.cat(outs)
         return out
+
+    def _exchange_slices(self, idx, dist_, task):
+        """One all-to-all of packed records (each rank receives the G partial lists of its own ceil(Q / G) queries),
+        slice-local merge + aggregation, one all-gather of the slice predictions."""
+        import torch
+        dist = _dist()
+        qb = idx.shape[0]
+        send = self.backend.pack_slices(idx, dist_, self.world)           # [G][slice_q][k+1][2]
+        slice_q = send.shape[1]
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        lo = min(qb, self.rank * slice_q)
+        mine = self.backend.merge_predict_packed(recv, min(qb, lo + slice_q) - lo, task)     # slice_q doubles
+        every = torch.empty(self.world * slice_q, dtype=torch.float64, device=mine.device)
+        dist.all_gather_into_tensor(every, mine, group=self.group)
+        return every[:qb]
+
+    def _exchange_all(self, idx, dist_, task):
+        """First-round form: all-gather of every rank's lists for ALL queries, every rank merges all of them."""
+        import torch
+        dist = _dist()
+        qb, ksel = idx.shape
+        all_idx = torch.empty((self.world * qb, ksel), dtype=idx.dtype, device=idx.device)
+        all_dist = torch.empty((self.world * qb, ksel), dtype=dist_.dtype, device=dist_.device)
+        dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(all_dist, dist_.contiguous(), group=self.group)
+        return self.backend.merge_predict(all_idx.view(self.world, qb, ksel),        # [part][q][k+1]
+                                          all_dist.view(self.world, qb, ksel), task, keep_on_device=True)
 
     def close(self):
         self.backend.close()

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(_native.LIB_PATH)
     for name in _declared_symbols() + _declared_symbols(SVM_HEADER, 'osml_svm_'):
         assert getattr(raw, name) is not None
-    assert lib.osml_knn_abi_version() == 1003
+    assert lib.osml_knn_abi_version() == 1004
 
 
 def test_enum_values_match_the_header():
@@ -72,7 +72,7 @@ def test_argument_validation_needs_no_gpu(lib):
         _native.check(_native.EINVAL)
     with pytest.raises(NotImplementedError):
         _native.check(_native.EUNSUPPORTED)
-    assert create(k=200, n=4, n_labels=300) in (_native.EUNSUPPORTED, _native.EINVAL)
+    assert create(k=2000, n=4, n_labels=3000) in (_native.EUNSUPPORTED, _native.EINVAL)   # k > 1024
 
 
 def test_create_fails_loudly_without_a_gpu(lib):

@@ -33,8 +33,7 @@ class OracleBackend:
             dst[i, :len(order)] = d[order]
         return torch.from_numpy(idx), torch.from_numpy(dst)
 
-    def merge_predict(self, parts_idx, parts_dist, task):
-        pi, pd_ = parts_idx.numpy(), parts_dist.numpy()
+    def _merge(self, pi, pd_, task):
         g, q, ksel = pi.shape
         flat_i = pi.transpose(1, 0, 2).reshape(q, g * ksel)
         flat_d = pd_.transpose(1, 0, 2).reshape(q, g * ksel)
@@ -45,6 +44,37 @@ class OracleBackend:
             out_i[i], out_d[i] = flat_i[i][order], flat_d[i][order]
         name = 'regression' if task == 0 else 'classification'
         return ko.predict_from_neighbours(out_i, out_d, self.labels, name, rbf_gamma=self.gamma)
+
+    def merge_predict(self, parts_idx, parts_dist, task, keep_on_device=False):
+        pred = self._merge(parts_idx.numpy(), parts_dist.numpy(), task)
+        return torch.from_numpy(pred) if keep_on_device else pred
+
+    # the record layout of include/osml_knn.h (osml_knn_pack_slices_device): [parts][slice_q][k+1] x {index, distance bits}
+    def pack_slices(self, idx, dist_, parts):
+        q, ksel = idx.shape
+        slice_q = -(-q // parts)
+        rec = np.empty((parts * slice_q, ksel, 2), dtype=np.int64)
+        rec[:, :, 0] = SENTINEL
+        d = dist_.numpy()
+        nan_bits = np.array([np.nan], dtype=d.dtype).view(np.uint32 if d.dtype == np.float32 else np.uint64)[0]
+        rec[:, :, 1] = int(nan_bits)
+        rec[:q, :, 0] = idx.numpy()
+        rec[:q, :, 1] = d.view(np.uint32 if d.dtype == np.float32 else np.uint64).astype(np.int64)
+        return torch.from_numpy(rec.reshape(parts, slice_q, ksel, 2))
+
+    def merge_predict_packed(self, records, q_valid, task):
+        rec = records.numpy()
+        parts, slice_q, ksel, _ = rec.shape
+        out = np.zeros(slice_q)
+        if q_valid > 0:
+            pi = rec[:, :q_valid, :, 0]
+            bits = np.ascontiguousarray(rec[:, :q_valid, :, 1])
+            if self.train.dtype == np.float32:
+                pd_ = bits.astype(np.uint32).view(np.float32)
+            else:
+                pd_ = bits.view(np.float64)
+            out[:q_valid] = self._merge(np.ascontiguousarray(pi), pd_, task)
+        return torch.from_numpy(out)
 
     def close(self):
         pass
@@ -70,8 +100,16 @@ def _worker(rank, world, port, results):
         for task, labels, name in ((1, labels_c, 'cls'), (0, labels_r, 'reg')):
             ix = sharded.TrainShardedIndex(train, labels, k, rbf_gamma=0.7, backend_factory=OracleBackend,
                                            query_block=16)
-            assert ix.bounds == [(0, 151), (151, 301)]
-            out['train_' + name] = ix.predict(queries, task)
+            assert ix.bounds == [(0, 151), (151, 301)] and ix.exchange == 'alltoall'
+            out['train_' + name] = ix.predict(queries, task)          # blocks of 16, 16 and 5 queries: odd last slice
+            ix = sharded.TrainShardedIndex(train, labels, k, rbf_gamma=0.7, backend_factory=OracleBackend,
+                                           query_block=16, exchange='allgather')
+            out['train_' + name + '_allgather'] = ix.predict(queries, task)
+        # float32 data (4-byte distances in the low word of a record), one query: rank 1's slice is empty
+        train32 = np.asfortranarray(train.astype(np.float32))
+        ix = sharded.TrainShardedIndex(train32, labels_c, k, rbf_gamma=0.7, backend_factory=OracleBackend)
+        out['train_cls_f32'] = ix.predict(queries.astype(np.float32), 1)
+        out['train_cls_f32_one'] = ix.predict(queries[:1].astype(np.float32), 1)
         # shard-local construction: each rank only passes its own rows (uneven split on purpose)
         lo, hi = (0, 100) if rank == 0 else (100, n)
         ix = sharded.TrainShardedIndex(train[lo:hi], labels_c, k, rbf_gamma=0.7, backend_factory=OracleBackend,
@@ -111,6 +149,12 @@ def test_world_size_2_sharded_paths_match_the_unsharded_oracle():
         got = results[rank]
         assert np.array_equal(got['train_cls'], want_c)
         assert np.array_equal(got['train_reg'], want_r)          # merge is exact: bit-identical to unsharded
+        assert np.array_equal(got['train_cls_allgather'], want_c)
+        assert np.array_equal(got['train_reg_allgather'], want_r)
+        want32 = ko.predict_classification(np.asfortranarray(train.astype(np.float32)), labels_c,
+                                           queries.astype(np.float32), k=k, rbf_gamma=0.7)
+        assert np.array_equal(got['train_cls_f32'], want32)
+        assert np.array_equal(got['train_cls_f32_one'], want32[:1])
         assert np.array_equal(got['train_cls_local'], want_c)
         assert np.array_equal(got['query'], want_c)
         assert np.array_equal(got['query_tiny'], want_c[:1])
