@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
 from oracle import knn_oracle as ko  # noqa: E402
-from oracle.ref_shim import import_reference  # noqa: E402
+from oracle.ref_shim import data_root, import_reference  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
 
@@ -78,7 +78,8 @@ def dataset_case(name, osp, ds, model, task):
 
 
 def main():
-    osp, osd, root = import_reference()
+    osp, osd, _ = import_reference()
+    root = data_root()
     os.makedirs(OUT, exist_ok=True)
     data = os.path.join(root, 'data')
 

@@ -21,7 +21,7 @@ import pandas as pd
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
-from oracle.ref_shim import import_reference  # noqa: E402
+from oracle.ref_shim import data_root, import_reference  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
 FIT_SEED = 7
@@ -95,7 +95,8 @@ def decision_case(name, osp, dtype, kernel, order, n, d, q, seed, int_range=5, *
 
 
 def main():
-    osp, osd, root = import_reference()
+    osp, osd, _ = import_reference()
+    root = data_root()
     os.makedirs(OUT, exist_ok=True)
     os.chdir(root)
     np.random.seed(0)

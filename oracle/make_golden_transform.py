@@ -14,13 +14,14 @@ import pandas as pd
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
-from oracle.ref_shim import import_reference  # noqa: E402
+from oracle.ref_shim import data_root, import_reference  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
 
 
 def main():
-    osp, osd, root = import_reference()
+    osp, osd, _ = import_reference()
+    root = data_root()
     import osml.transform as ost
     rng = np.random.default_rng(77)
     cases = {}

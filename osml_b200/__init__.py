@@ -9,14 +9,14 @@ in front of kNN (``Centering``, ``Standardization``: osml/transform.py:53-84), w
 SMO error cache) behind ``include/osml_svm.h``.  There is no CPU fallback: without the built library and a CUDA device
 ``fit`` raises.
 """
-from osml_b200.model import Model, load, save, is_categorical, is_continuous  # noqa: F401
+from osml_b200.model import Model, load, save, is_categorical, is_continuous, reference_modules  # noqa: F401
 from osml_b200.predict import (  # noqa: F401
     ClassificationModel, KNearestNeighbors, KNearestNeighborsClassification, KNearestNeighborsRegression,
-    PredictiveModel, RegressionModel)
+    PredictiveModel, RegressionModel, from_reference, to_reference)
 from osml_b200.svm import BinaryClassificationModel, SupportVectorMachine  # noqa: F401
 from osml_b200.transform import Centering, Standardization, TransformativeModel  # noqa: F401
 
 __all__ = ['Model', 'PredictiveModel', 'RegressionModel', 'ClassificationModel', 'KNearestNeighbors',
            'KNearestNeighborsRegression', 'KNearestNeighborsClassification', 'save', 'load', 'is_continuous',
            'is_categorical', 'TransformativeModel', 'Centering', 'Standardization', 'BinaryClassificationModel',
-           'SupportVectorMachine']
+           'SupportVectorMachine', 'reference_modules', 'to_reference', 'from_reference']

@@ -52,6 +52,11 @@ class Stats(ctypes.Structure):
 _lib = None
 
 
+def library_path():
+    """Where the C-ABI library lives (what a binding in the reference would hand to ctypes.CDLL)."""
+    return LIB_PATH
+
+
 def lib():
     """Loads libosml_knn.so once.  No fallback: raises ImportError if it has not been built."""
     global _lib

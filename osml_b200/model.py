@@ -3,9 +3,57 @@
 Same template method (``fit`` records dtypes and label metadata, validates, then calls the ``_fit`` hook), same bare
 ``ValueError`` at the same conditions, same pickle-based ``save`` / ``load``.
 """
+import importlib
+import os
 import pickle
+import sys
 
 import numpy as np
+
+
+def reference_modules():
+    """The reference's own ``osml.model`` / ``osml.predict`` / ``osml.transform`` when that package is importable --
+    installed next to this one, or at ``$OSML_REF`` -- else ``None``.
+
+    When it is there, every class of this package is built ON the reference's class of the same name (see ``_base``),
+    so the ``isinstance(base_model, PredictiveModel / RegressionModel / ClassificationModel)`` checks of the reference's
+    meta-models (osml/predict.py:1326, 1393, 1410, 1427) accept a GPU model as their base model.  Every method of the
+    contract is overridden here, so behaviour does not depend on which base was picked.
+    ``OSML_B200_STANDALONE=1`` forces the standalone bases."""
+    if os.environ.get('OSML_B200_STANDALONE'):
+        return None
+    if 'mods' not in _REFERENCE:
+        _REFERENCE['mods'] = _import_reference()
+    return _REFERENCE['mods']
+
+
+_REFERENCE = {}
+
+
+def _import_reference():
+    def attempt():
+        mods = tuple(importlib.import_module('osml.' + name) for name in ('model', 'predict', 'transform'))
+        ok = all(hasattr(mods[1], name) for name in ('PredictiveModel', 'RegressionModel', 'ClassificationModel'))
+        return mods if ok and hasattr(mods[0], 'Model') else None
+    try:
+        return attempt()
+    except Exception:
+        pass
+    root = os.environ.get('OSML_REF')
+    if root and os.path.isfile(os.path.join(root, 'osml', 'predict.py')):
+        sys.path.append(root)
+        try:
+            return attempt()
+        except Exception:
+            pass
+        sys.path.remove(root)
+    return None
+
+
+def _base(module_index, name):
+    """The reference class to build on, or ``object``."""
+    mods = reference_modules()
+    return getattr(mods[module_index], name, object) if mods else object
 
 
 def is_continuous(data_type):
@@ -18,7 +66,7 @@ def is_categorical(data_type):
     return np.issubdtype(data_type, np.integer)
 
 
-class Model:
+class Model(_base(0, 'Model')):
     """Base of every model (osml/model.py:7-59)."""
 
     def __init__(self, epsilon):
@@ -68,14 +116,22 @@ class Model:
         return self._fit(observations_df, labels_sr)
 
 
-def save(model, file_path):
+def save(model, file_path, portable=False):
     """Pickles the model to ``file_path`` (osml/model.py:62-71).  Device handles are dropped by the model's
-    ``__getstate__``; the logical state matches the reference's (``_observations``, ``_labels``, ``k``, ...)."""
+    ``__getstate__``; the logical state matches the reference's (``_observations``, ``_labels``, ``k``, ...).
+    ``portable=True`` writes a kNN model as the REFERENCE's class (``osml.predict.KNearestNeighbors*``, see
+    ``osml_b200.predict.to_reference``), so the file also loads where only the reference is installed."""
+    if portable:
+        from osml_b200.predict import to_reference
+        model = to_reference(model)
     with open(file_path, mode='wb') as file:
         pickle.dump(model, file)
 
 
 def load(file_path):
-    """Inverse of ``save`` (osml/model.py:74-85)."""
+    """Inverse of ``save`` (osml/model.py:74-85).  A file that holds the reference's CPU kNN model (written by the
+    reference's own ``save``, or by ``save(..., portable=True)``) comes back as the GPU model with the same state."""
     with open(file_path, mode='rb') as file:
-        return pickle.load(file)
+        model = pickle.load(file)
+    from osml_b200.predict import from_reference, is_reference_knn
+    return from_reference(model) if is_reference_knn(model) else model

@@ -22,7 +22,7 @@ import osml_b200.model as osm
 from osml_b200 import _native
 
 
-class PredictiveModel(osm.Model):
+class PredictiveModel(osm.Model, osm._base(1, 'PredictiveModel')):
     """Abstract predictive model (osml/predict.py:13-89)."""
 
     def __init__(self, epsilon=1e-8):
@@ -59,7 +59,7 @@ class PredictiveModel(osm.Model):
         return self._test(observations_df, labels_sr)
 
 
-class RegressionModel(PredictiveModel):
+class RegressionModel(PredictiveModel, osm._base(1, 'RegressionModel')):
     """Regression base (osml/predict.py:92-106)."""
 
     def __init__(self):
@@ -75,7 +75,7 @@ class RegressionModel(PredictiveModel):
         return np.sqrt(np.square(predictions_sr.values - labels_sr.values).mean())
 
 
-class ClassificationModel(PredictiveModel):
+class ClassificationModel(PredictiveModel, osm._base(1, 'ClassificationModel')):
     """Classification base (osml/predict.py:264-278)."""
 
     def __init__(self):
@@ -221,3 +221,42 @@ class KNearestNeighborsClassification(KNearestNeighbors, ClassificationModel):
     def __init__(self, k=7, rbf_gamma=1):
         KNearestNeighbors.__init__(self, k, rbf_gamma)
         ClassificationModel.__init__(self)
+
+
+# -- cross-install pickles (osml/model.py:62-85) ------------------------------------------------
+_STATE = ('epsilon', '_observation_types', '_label_type', '_label_name', 'k', 'rbf_gamma', '_observations_mean',
+          '_observations_sd', '_observations', '_labels')
+
+
+def is_reference_knn(model):
+    """True for an instance of the reference's own CPU classes osml.predict.KNearestNeighbors{Regression,Classification}."""
+    cls = type(model)
+    return cls.__module__ == 'osml.predict' and cls.__name__ in ('KNearestNeighborsRegression',
+                                                                  'KNearestNeighborsClassification')
+
+
+def to_reference(model):
+    """The reference's CPU model (``osml.predict.KNearestNeighbors*``) with this model's logical state -- what the
+    reference's own ``fit`` on the same frame would have left (predict.py:733-738, 770-771; model.py:14-17).  Needs the
+    reference package (``reference_modules()``); the result pickles without any trace of this package."""
+    mods = osm.reference_modules()
+    if mods is None:
+        raise ImportError('the reference package (osml) is not importable: set OSML_REF or install it')
+    if not isinstance(model, KNearestNeighbors):
+        raise ValueError
+    cls = getattr(mods[1], type(model).__name__)
+    twin = cls(k=model.k, rbf_gamma=model.rbf_gamma)
+    for name in _STATE:
+        setattr(twin, name, getattr(model, name))
+    return twin
+
+
+def from_reference(model):
+    """The GPU model with the state of a reference CPU kNN model (fitted or not); the device index is built lazily."""
+    if not is_reference_knn(model):
+        raise ValueError
+    cls = KNearestNeighborsRegression if type(model).__name__.endswith('Regression') else KNearestNeighborsClassification
+    twin = cls(k=model.k, rbf_gamma=model.rbf_gamma)
+    for name in _STATE:
+        setattr(twin, name, getattr(model, name))
+    return twin

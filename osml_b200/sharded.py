@@ -77,14 +77,19 @@ class NativeBackend:
             self.index.neighbours_device(d_q.data_ptr(), q, idx.data_ptr(), dist.data_ptr(), stream)
         return idx, dist
 
-    def merge_predict(self, parts_idx, parts_dist, task, keep_on_device=False):
+    def merge_predict(self, parts_idx, parts_dist, task, keep_on_device=False, return_lists=False):
         torch = self.torch
-        parts, q = parts_idx.shape[0], parts_idx.shape[1]
+        parts, q, ksel = parts_idx.shape
         with torch.cuda.device(self.device):
             pred = torch.empty(q, dtype=torch.float64, device=self.device)
+            m_idx = torch.empty((q, ksel), dtype=torch.int64, device=self.device) if return_lists else None
+            m_dist = torch.empty((q, ksel), dtype=self.dist_dtype, device=self.device) if return_lists else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self.index.merge_predict_device(parts_idx.data_ptr(), parts_dist.data_ptr(), parts, q, task,
-                                            pred.data_ptr(), None, None, stream)
+                                            pred.data_ptr(), m_idx.data_ptr() if return_lists else None,
+                                            m_dist.data_ptr() if return_lists else None, stream)
+            if return_lists:
+                return pred, m_idx, m_dist
             return pred if keep_on_device else pred.cpu().numpy()
 
     def pack_slices(self, idx, dist, parts):
@@ -99,18 +104,22 @@ class NativeBackend:
             self.index.pack_slices_device(idx.data_ptr(), dist.data_ptr(), q, parts, records.data_ptr(), stream)
         return records
 
-    def merge_predict_packed(self, records, q_valid, task):
+    def merge_predict_packed(self, records, q_valid, task, return_lists=False):
         """records [parts, slice_q, k+1, 2] = every rank's partial lists of this rank's slice -> fp64 predictions of
-        the slice as a tensor of slice_q entries (the first q_valid are meaningful)."""
+        the slice as a tensor of slice_q entries (the first q_valid are meaningful); with return_lists also the merged
+        (index, distance) lists, slice_q rows each."""
         torch = self.torch
-        parts, slice_q = records.shape[0], records.shape[1]
+        parts, slice_q, ksel = records.shape[0], records.shape[1], records.shape[2]
         with torch.cuda.device(self.device):
             pred = torch.zeros(slice_q, dtype=torch.float64, device=self.device)
+            m_idx = torch.zeros((slice_q, ksel), dtype=torch.int64, device=self.device) if return_lists else None
+            m_dist = torch.zeros((slice_q, ksel), dtype=self.dist_dtype, device=self.device) if return_lists else None
             if q_valid > 0:
                 stream = torch.cuda.current_stream(self.device).cuda_stream
                 self.index.merge_predict_packed_device(records.data_ptr(), parts, slice_q, q_valid, task,
-                                                       pred.data_ptr(), None, None, stream)
-        return pred
+                                                       pred.data_ptr(), m_idx.data_ptr() if return_lists else None,
+                                                       m_dist.data_ptr() if return_lists else None, stream)
+        return (pred, m_idx, m_dist) if return_lists else pred
 
     def close(self):
         self.index.close()
@@ -154,35 +163,34 @@ class TrainShardedIndex:
             raise ValueError
         self.exchange = exchange
 
-    def predict(self, queries, task, keep_on_device=False):
+    def predict(self, queries, task, keep_on_device=False, return_neighbours=False):
         """queries: the same (Q, D) matrix on every rank (host array, or a CUDA tensor on this rank's device).
-        Returns the fp64 predictions for all Q on every rank (a CUDA tensor with keep_on_device)."""
+        Returns the fp64 predictions for all Q on every rank (a CUDA tensor with keep_on_device); with
+        return_neighbours also the merged global (index, distance) lists, (Q, k+1) each."""
         on_device = not isinstance(queries, np.ndarray) and hasattr(queries, 'data_ptr')
         if not on_device:
             queries = np.asarray(queries)
         if self.n < self.k + 2:
             raise ValueError                                  # np.argpartition(d, k + 1) needs k + 1 < N
         outs = []
-        out = None if keep_on_device else np.empty(queries.shape[0], dtype=np.float64)
         for q0 in range(0, queries.shape[0], self.query_block):
             block = queries[q0:q0 + self.query_block]
             idx, dist_ = self.backend.neighbours(block)
             if self.world > 1 and self.exchange == 'alltoall':
-                pred = self._exchange_slices(idx, dist_, task)
+                res = self._exchange_slices(idx, dist_, task, return_neighbours)
             elif self.world > 1:
-                pred = self._exchange_all(idx, dist_, task)
+                res = self._exchange_all(idx, dist_, task, return_neighbours)
             else:
-                pred = self.backend.merge_predict(idx[None], dist_[None], task, keep_on_device=True)
-            if keep_on_device:
-                outs.append(pred)
-            else:
-                out[q0:q0 + block.shape[0]] = pred.cpu().numpy()
-        if keep_on_device:
-            import torch
-            return outs[0] if len(outs) == 1 else torch.cat(outs)
-        return out
+                res = self.backend.merge_predict(idx[None], dist_[None], task, keep_on_device=True,
+                                                 return_lists=return_neighbours)
+            outs.append(res if return_neighbours else (res,))
+        import torch
+        cols = [outs[0][c] if len(outs) == 1 else torch.cat([o[c] for o in outs]) for c in range(len(outs[0]))]
+        if not keep_on_device:
+            cols = [c.cpu().numpy() for c in cols]
+        return tuple(cols) if return_neighbours else cols[0]
 
-    def _exchange_slices(self, idx, dist_, task):
+    def _exchange_slices(self, idx, dist_, task, want_lists=False):
         """One all-to-all of packed records (each rank receives the G partial lists of its own ceil(Q / G) queries),
         slice-local merge + aggregation, one all-gather of the slice predictions."""
         import torch
@@ -193,12 +201,15 @@ class TrainShardedIndex:
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv, send, group=self.group)
         lo = min(qb, self.rank * slice_q)
-        mine = self.backend.merge_predict_packed(recv, min(qb, lo + slice_q) - lo, task)     # slice_q doubles
-        every = torch.empty(self.world * slice_q, dtype=torch.float64, device=mine.device)
-        dist.all_gather_into_tensor(every, mine, group=self.group)
-        return every[:qb]
+        mine = self.backend.merge_predict_packed(recv, min(qb, lo + slice_q) - lo, task, return_lists=want_lists)
+        gathered = []
+        for part in (mine if want_lists else (mine,)):                    # slice_q rows each
+            every = torch.empty((self.world * slice_q,) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
+            dist.all_gather_into_tensor(every, part.contiguous(), group=self.group)
+            gathered.append(every[:qb])
+        return tuple(gathered) if want_lists else gathered[0]
 
-    def _exchange_all(self, idx, dist_, task):
+    def _exchange_all(self, idx, dist_, task, want_lists=False):
         """First-round form: all-gather of every rank's lists for ALL queries, every rank merges all of them."""
         import torch
         dist = _dist()
@@ -208,7 +219,8 @@ class TrainShardedIndex:
         dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=self.group)
         dist.all_gather_into_tensor(all_dist, dist_.contiguous(), group=self.group)
         return self.backend.merge_predict(all_idx.view(self.world, qb, ksel),        # [part][q][k+1]
-                                          all_dist.view(self.world, qb, ksel), task, keep_on_device=True)
+                                          all_dist.view(self.world, qb, ksel), task, keep_on_device=True,
+                                          return_lists=want_lists)
 
     def close(self):
         self.backend.close()

@@ -24,7 +24,7 @@ from osml_b200 import _native
 from osml_b200.predict import PredictiveModel, _default_device
 
 
-class BinaryClassificationModel(PredictiveModel):
+class BinaryClassificationModel(PredictiveModel, osm._base(1, 'BinaryClassificationModel')):
     """Binary classification base (osml/predict.py:109-262): labels are integers in {0, 1}; ``_fuzzy_predict`` gives
     the positive-class membership in [0, 1] and ``predict`` rounds it."""
 

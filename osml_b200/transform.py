@@ -19,7 +19,7 @@ import osml_b200.model as osm
 from osml_b200 import _native
 
 
-class TransformativeModel(osm.Model):
+class TransformativeModel(osm.Model, osm._base(2, 'TransformativeModel')):
     """Abstract data transformation model (osml/transform.py:9-50)."""
 
     def __init__(self, epsilon=1e-8):

@@ -9,6 +9,13 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 
+# When the reference package is reachable (baseline/_ref travels to the GPU box; /root/reference exists in the authoring
+# container only) the GPU classes are built on the reference's bases (osml_b200.model.reference_modules), which is what
+# the meta-model tests need.  Must be set before osml_b200 is first imported.
+for _root in (os.path.join(ROOT, 'baseline', '_ref'), '/root/reference'):
+    if 'OSML_REF' not in os.environ and os.path.isfile(os.path.join(_root, 'osml', 'predict.py')):
+        os.environ['OSML_REF'] = _root
+
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a real B200 (run with -m gpu on the GPU box)')

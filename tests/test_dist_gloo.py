@@ -43,10 +43,12 @@ class OracleBackend:
             order = np.lexsort((flat_i[i], flat_d[i]))[:ksel]     # NaN sorts last, then by index
             out_i[i], out_d[i] = flat_i[i][order], flat_d[i][order]
         name = 'regression' if task == 0 else 'classification'
-        return ko.predict_from_neighbours(out_i, out_d, self.labels, name, rbf_gamma=self.gamma)
+        return ko.predict_from_neighbours(out_i, out_d, self.labels, name, rbf_gamma=self.gamma), out_i, out_d
 
-    def merge_predict(self, parts_idx, parts_dist, task, keep_on_device=False):
-        pred = self._merge(parts_idx.numpy(), parts_dist.numpy(), task)
+    def merge_predict(self, parts_idx, parts_dist, task, keep_on_device=False, return_lists=False):
+        pred, out_i, out_d = self._merge(parts_idx.numpy(), parts_dist.numpy(), task)
+        if return_lists:
+            return torch.from_numpy(pred), torch.from_numpy(out_i), torch.from_numpy(out_d)
         return torch.from_numpy(pred) if keep_on_device else pred
 
     # the record layout of include/osml_knn.h (osml_knn_pack_slices_device): [parts][slice_q][k+1] x {index, distance bits}
@@ -62,18 +64,20 @@ class OracleBackend:
         rec[:q, :, 1] = d.view(np.uint32 if d.dtype == np.float32 else np.uint64).astype(np.int64)
         return torch.from_numpy(rec.reshape(parts, slice_q, ksel, 2))
 
-    def merge_predict_packed(self, records, q_valid, task):
+    def merge_predict_packed(self, records, q_valid, task, return_lists=False):
         rec = records.numpy()
         parts, slice_q, ksel, _ = rec.shape
+        f32 = self.train.dtype == np.float32
         out = np.zeros(slice_q)
+        out_i = np.zeros((slice_q, ksel), np.int64)
+        out_d = np.zeros((slice_q, ksel), np.float32 if f32 else np.float64)
         if q_valid > 0:
             pi = rec[:, :q_valid, :, 0]
             bits = np.ascontiguousarray(rec[:, :q_valid, :, 1])
-            if self.train.dtype == np.float32:
-                pd_ = bits.astype(np.uint32).view(np.float32)
-            else:
-                pd_ = bits.view(np.float64)
-            out[:q_valid] = self._merge(np.ascontiguousarray(pi), pd_, task)
+            pd_ = bits.astype(np.uint32).view(np.float32) if f32 else bits.view(np.float64)
+            out[:q_valid], out_i[:q_valid], out_d[:q_valid] = self._merge(np.ascontiguousarray(pi), pd_, task)
+        if return_lists:
+            return torch.from_numpy(out), torch.from_numpy(out_i), torch.from_numpy(out_d)
         return torch.from_numpy(out)
 
     def close(self):
@@ -110,6 +114,7 @@ def _worker(rank, world, port, results):
         ix = sharded.TrainShardedIndex(train32, labels_c, k, rbf_gamma=0.7, backend_factory=OracleBackend)
         out['train_cls_f32'] = ix.predict(queries.astype(np.float32), 1)
         out['train_cls_f32_one'] = ix.predict(queries[:1].astype(np.float32), 1)
+        out['train_cls_f32_lists'] = ix.predict(queries.astype(np.float32), 1, return_neighbours=True)
         # shard-local construction: each rank only passes its own rows (uneven split on purpose)
         lo, hi = (0, 100) if rank == 0 else (100, n)
         ix = sharded.TrainShardedIndex(train[lo:hi], labels_c, k, rbf_gamma=0.7, backend_factory=OracleBackend,
@@ -155,6 +160,11 @@ def test_world_size_2_sharded_paths_match_the_unsharded_oracle():
                                            queries.astype(np.float32), k=k, rbf_gamma=0.7)
         assert np.array_equal(got['train_cls_f32'], want32)
         assert np.array_equal(got['train_cls_f32_one'], want32[:1])
+        _, want_i, want_d = ko.predict_classification(np.asfortranarray(train.astype(np.float32)), labels_c,
+                                                      queries.astype(np.float32), k=k, rbf_gamma=0.7,
+                                                      return_neighbours=True)
+        pred, got_i, got_d = got['train_cls_f32_lists']
+        assert np.array_equal(pred, want32) and np.array_equal(got_i, want_i) and np.array_equal(got_d, want_d)
         assert np.array_equal(got['train_cls_local'], want_c)
         assert np.array_equal(got['query'], want_c)
         assert np.array_equal(got['query_tiny'], want_c[:1])
