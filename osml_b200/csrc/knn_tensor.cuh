@@ -45,6 +45,12 @@
 #ifndef OSML_TC_COUNTERS
 #define OSML_TC_COUNTERS 0
 #endif
+// -DOSML_TC_DEBUG=1 keeps the profiling ablations of the K1 kernels (TcParams::debug); the product compiles them out --
+// each test was a constant-bank load and a branch per tile on the epilogue's critical path
+#ifndef OSML_TC_DEBUG
+#define OSML_TC_DEBUG 0
+#endif
+#define OSML_TC_DBG(p) (OSML_TC_DEBUG ? (p).debug : 0)
 
 namespace osml {
 
@@ -606,7 +612,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     for (int kb = 0; kb < p.nkb; ++kb) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                         unsigned char* ring = b_smem + (size_t)stage * ring_stage_bytes;
-                        if (p.debug == 3) {                      // ablation: no operand traffic, MMA on stale smem
+                        if (OSML_TC_DBG(p) == 3) {                      // ablation: no operand traffic, MMA on stale smem
                             ptx::mbar_arrive(&full_bar[stage]);
                         } else {
                             ptx::mbar_expect_tx(&full_bar[stage], ring_stage_bytes);
@@ -676,25 +682,25 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int tile0 = seg;                                   // segments interleave: tiles seg, seg + nseg, ...
                 const int ntiles = (p.tiles_total - seg + p.nseg - 1) / p.nseg;
                 list.reset();
-                if (p.debug == 4) list.thr = INFINITY;   // ablation: fast path only
+                if (OSML_TC_DBG(p) == 4) list.thr = INFINITY;   // ablation: fast path only
                 for (int t = 0; t < ntiles; ++t, ++acc_it) {
                     const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
                     ptx::mbar_wait(&tmem_full[as], aphase);
                     ptx::tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
                     const int row_base = (tile0 + t * p.nseg) * kTcBN + half * cols;
-                    if (p.debug != 1 && p.debug != 3) {
+                    if (OSML_TC_DBG(p) != 1 && OSML_TC_DBG(p) != 3) {
                         if constexpr (KP <= 16) {
                             float va[32], vb[32];
                             ptx::tmem_ld_32x32(taddr, va);
                             for (int c = 0; c < cols; c += 64) {   // two chunks per trip, loads one chunk ahead
                                 ptx::tmem_ld_wait();
                                 ptx::tmem_ld_32x32(taddr + c + 32, vb);
-                                if (p.debug != 2) list.scan(va, row_base + c, p.h, p.hmin8);
+                                if (OSML_TC_DBG(p) != 2) list.scan(va, row_base + c, p.h, p.hmin8);
                                 else if (va[0] + va[31] == 12345.678f) list.thr = va[0];
                                 ptx::tmem_ld_wait();
                                 if (c + 64 < cols) ptx::tmem_ld_32x32(taddr + c + 64, va);
-                                if (p.debug != 2) list.scan(vb, row_base + c + 32, p.h, p.hmin8);
+                                if (OSML_TC_DBG(p) != 2) list.scan(vb, row_base + c + 32, p.h, p.hmin8);
                                 else if (vb[0] + vb[31] == 12345.678f) list.thr = vb[0];
                             }
                         } else {
@@ -756,16 +762,16 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kTcBN + half * cols;
                     const int row_base = (tile0 + t * p.nseg) * kTcBN + half * cols;
                     float va[32], vb[32];
-                    if (p.debug != 1 && p.debug != 3) {
+                    if (OSML_TC_DBG(p) != 1 && OSML_TC_DBG(p) != 3) {
                         ptx::tmem_ld_32x32(taddr, va);
                         for (int c = 0; c < cols; c += 64) {      // two 32-column chunks per trip, loads one chunk ahead
                             ptx::tmem_ld_wait();
                             ptx::tmem_ld_32x32(taddr + c + 32, vb);
-                            if (p.debug != 2) scan(va, row_base + c);
+                            if (OSML_TC_DBG(p) != 2) scan(va, row_base + c);
                             else if (va[0] + va[31] == 12345.678f) thr = va[0];
                             ptx::tmem_ld_wait();
                             if (c + 64 < cols) ptx::tmem_ld_32x32(taddr + c + 64, va);
-                            if (p.debug != 2) scan(vb, row_base + c + 32);
+                            if (OSML_TC_DBG(p) != 2) scan(vb, row_base + c + 32);
                             else if (vb[0] + vb[31] == 12345.678f) thr = vb[0];
                         }
                     }
@@ -810,22 +816,32 @@ constexpr int kTcBHalfBytes = (kTcBN / 2) * 128;      // 16 KB: this CTA's half 
 // Work items of the pair kernel.  Query-tile pairs 0 .. nq_single-1 are swept over the whole train set in ONE item
 // (one warm-up of the candidate lists, the tightest thresholds); the remaining pairs -- those that would leave most of
 // the machine idle in a last partial wave -- are split into nseg interleaved segments (tiles seg, seg + nseg, ...).
+// The split items are numbered segment-major (all pairs' segment 0, then all pairs' segment 1, ...): by the time a
+// later segment of a query starts, its earlier segments have usually finished and their thresholds seed its lists.
 struct TcItem { int qp, seg, nsg; };
 __device__ __forceinline__ TcItem tc_pair_item(const TcParams& p, int item) {
     TcItem r;
     if (item < p.nq_single) { r.qp = item; r.seg = 0; r.nsg = 1; }
-    else { const int j = item - p.nq_single; r.qp = p.nq_single + j / p.nseg; r.seg = j % p.nseg; r.nsg = p.nseg; }
+    else {
+        const int j = item - p.nq_single, nrest = p.nqt / 2 - p.nq_single;
+        r.qp = p.nq_single + j % nrest; r.seg = j / nrest; r.nsg = p.nseg;
+    }
     return r;
 }
 
-template <int KP>
+// kWide (rows too long for a resident query tile next to two whole half-tile stages: D > 253): the ring works at K-block
+// granularity instead -- a stage holds [this CTA's 128 x 64 query block][its 128 x 64 half of the train block], one
+// barrier round trip per K block, one issuer thread (a tile takes thousands of MMA cycles, its bookkeeping is noise).
+// Everything else -- the CTA pair's M = 256 MMA that halves the L2 -> shared-memory traffic per FLOP of the single-CTA
+// kernel, the staged epilogue with early TMEM release, the h ring, threshold seeding -- is the same code.
+template <int KP, bool kWide>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                           const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_smem = smem;
-    unsigned char* b_smem = a_smem + (size_t)p.nkb * kTcABlockBytes;
-    const uint32_t stage_bytes = (uint32_t)p.nkb * kTcBHalfBytes;
+    unsigned char* b_smem = a_smem + (kWide ? (size_t)0 : (size_t)p.nkb * kTcABlockBytes);
+    const uint32_t stage_bytes = kWide ? (uint32_t)(kTcABlockBytes + kTcBHalfBytes) : (uint32_t)p.nkb * kTcBHalfBytes;
     const int epi_threads = p.epi_warps * 32;
     unsigned char* cand_buf = b_smem + (size_t)p.stages * stage_bytes;         // [kTcBufCap][epi_threads] x 8 B
     unsigned char* h_ring = cand_buf + (size_t)kTcBufCap * epi_threads * 8;     // [kTcHSlots][kTcHBlock] floats
@@ -878,11 +894,13 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     const int seg = wi.seg, nsg = wi.nsg, qt = 2 * wi.qp + (int)rank;
                     const int tile0 = seg;
                     const int ntiles = (p.tiles_total - seg + nsg - 1) / nsg;
-                    ptx::mbar_wait(a_empty, (it & 1) ^ 1);
-                    if (leader) ptx::mbar_expect_tx(a_full, 2u * (uint32_t)p.nkb * kTcABlockBytes);
-                    else ptx::mbar_arrive_remote(a_full, 0);
-                    for (int kb = 0; kb < p.nkb; ++kb)
-                        ptx::tma_load_2d_pair(a_smem + (size_t)kb * kTcABlockBytes, &map_a, a_full, kb * kTcKB, qt * kTcBM);
+                    if (!kWide) {
+                        ptx::mbar_wait(a_empty, (it & 1) ^ 1);
+                        if (leader) ptx::mbar_expect_tx(a_full, 2u * (uint32_t)p.nkb * kTcABlockBytes);
+                        else ptx::mbar_arrive_remote(a_full, 0);
+                        for (int kb = 0; kb < p.nkb; ++kb)
+                            ptx::tma_load_2d_pair(a_smem + (size_t)kb * kTcABlockBytes, &map_a, a_full, kb * kTcKB, qt * kTcBM);
+                    }
                     for (int t = 0; t < ntiles; ++t) {
                         const int row0 = (tile0 + t * nsg) * kTcBN + (int)rank * (kTcBN / 2);
                         // this CTA's copy of the tile's h block (256 x h, 32 group minima) for its epilogue warps
@@ -891,8 +909,20 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                         ptx::bulk_load_1d(h_ring + (size_t)hslot * kTcHBlock * 4, p.hblk + (size_t)(tile0 + t * nsg) * kTcHBlock,
                                           kTcHBlock * 4, &h_full[hslot]);
                         if (++hslot == (uint32_t)kTcHSlots) { hslot = 0; hphase ^= 1; }
+                        if (kWide) {
+                            for (int kb = 0; kb < p.nkb; ++kb) {     // one stage per K block: query block + train half block
+                                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                                if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+                                else ptx::mbar_arrive_remote(&full_bar[stage], 0);
+                                unsigned char* ring = b_smem + (size_t)stage * stage_bytes;
+                                ptx::tma_load_2d_pair(ring, &map_a, &full_bar[stage], kb * kTcKB, qt * kTcBM);
+                                ptx::tma_load_2d_pair(ring + kTcABlockBytes, &map_b, &full_bar[stage], kb * kTcKB, row0);
+                                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                            }
+                            continue;
+                        }
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        if (p.debug == 3) {                          // ablation: no operand traffic
+                        if (OSML_TC_DBG(p) == 3) {                          // ablation: no operand traffic
                             if (leader) ptx::mbar_arrive(&full_bar[stage]);
                             else ptx::mbar_arrive_remote(&full_bar[stage], 0);
                         } else {
@@ -906,7 +936,39 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     }
                 }
             }
-        } else if (warp == 1 || warp == 3) {
+        } else if (kWide && warp == 1) {
+            if (lane == 0 && leader) {
+                // ===== MMA issuer (leader CTA only), K-block granular ring =====
+                const uint32_t idesc = (p.f16 ? ptx::umma_idesc_f16(2 * kTcBM, kTcBN) : ptx::umma_idesc_bf16(2 * kTcBM, kTcBN));
+                const uint32_t hi = ptx::umma_desc_hi_k_sw128();
+                const uint32_t ring_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_smem));
+                uint32_t stage = 0, phase = 0, acc_it = 0;
+                for (int item = cluster_id; item < nitems; item += nclusters) {
+                    const TcItem wi = tc_pair_item(p, item);
+                    const int ntiles = (p.tiles_total - wi.seg + wi.nsg - 1) / wi.nsg;
+                    for (int t = 0; t < ntiles; ++t, ++acc_it) {
+                        const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                        ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+                        const uint32_t tmem_d = tmem_base + as * kTcBN;
+                        for (int kb = 0; kb < p.nkb; ++kb) {
+                            ptx::mbar_wait(&full_bar[stage], phase);
+                            ptx::tc_fence_after();
+                            const int nks = p.ksteps - kb * 4;
+                            const uint32_t a_lo = ring_lo0 + stage * (stage_bytes >> 4);
+                            const uint32_t b_lo = a_lo + (kTcABlockBytes >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                if (ks < nks)
+                                    ptx::umma_bf16_ss_pair_lohi(tmem_d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc,
+                                                                (uint32_t)((kb | ks) != 0));
+                            ptx::umma_commit_pair(&empty_bar[stage]);      // both CTAs may refill this stage
+                            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                        }
+                        ptx::umma_commit_pair(&tmem_full[as]);             // both CTAs' epilogues may read the tile
+                    }
+                }
+            }
+        } else if (!kWide && (warp == 1 || warp == 3)) {
             if (lane == 0 && leader) {
                 // ===== MMA issuers (leader CTA only) =====
                 // Two threads, one per accumulator stage: issuer 0 (warp 1) takes the even tiles, issuer 1 (warp 3) the
@@ -997,6 +1059,18 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const uint32_t hm_base = ptx::smem_u32(h_ring) + kTcBN * 4 + (uint32_t)(half * cols / 8) * 4u;   // their group minima
             const uint32_t hmin_base = ptx::smem_u32(h_ring) + (kTcBN + kTcBN / 8 + (cols == 128 ? half : 2)) * 4;  // their minimum
             const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * cols);
+            const uint32_t lane0 = lane == 0 ? 1u : 0u;
+            // made opaque to the compiler: it would otherwise re-derive each of these from %tid / the kernel parameters
+            // once per tile (S2R, constant-bank loads and dependent integer chains in front of the TMEM loads)
+            {
+                uint32_t* keep[] = {const_cast<uint32_t*>(&bar_tmem_full), const_cast<uint32_t*>(&bar_tmem_empty),
+                                    const_cast<uint32_t*>(&bar_h_full), const_cast<uint32_t*>(&bar_h_empty),
+                                    const_cast<uint32_t*>(&h_base), const_cast<uint32_t*>(&hm_base),
+                                    const_cast<uint32_t*>(&hmin_base), const_cast<uint32_t*>(&taddr0),
+                                    const_cast<uint32_t*>(&lane0)};
+#pragma unroll
+                for (uint32_t* r : keep) asm volatile("mov.b32 %0, %0;" : "+r"(*r));
+            }
             long long dbg_epi_wait = 0, dbg_epi_drain = 0, dbg_epi_hits = 0, dbg_epi_hit_tiles = 0, dbg_epi_load = 0, dbg_big_cyc = 0, dbg_big_cnt = 0, dbg_mid_cyc = 0, dbg_mid_cnt = 0;
             const long long dbg_e0 = clock64();
             for (int item = cluster_id; item < nitems; item += nclusters) {
@@ -1013,7 +1087,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 for (int s2 = 0; s2 < seg; ++s2)
                     seed = fmaxf(seed, *(const volatile float*)(p.cand_thr + q * p.nslot + (size_t)s2 * halves + half));
                 list.reset(seed, p.kactive);
-                if (p.debug == 4) list.thr = INFINITY;       // ablation: fast path only
+                if (OSML_TC_DBG(p) == 4) list.thr = INFINITY;       // ablation: fast path only
                 int row_base = tile0 * kTcBN + half * cols;
                 for (int t = 0; t < ntiles; ++t, ++acc_it, row_base += nsg * kTcBN) {
                     const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
@@ -1028,7 +1102,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     ptx::mbar_wait_addr(bar_h_full + hslot * 8, hphase);
                     const uint32_t hs = hslot * (kTcHBlock * 4);
                     bool released = false;
-                    if (p.debug != 1 && p.debug != 3) {
+                    if (OSML_TC_DBG(p) != 1 && OSML_TC_DBG(p) != 3) {
                         if (cols == 128) {
                             // the thread's whole 128-column share of the tile moves to registers in one go and the
                             // accumulator stage goes straight back to the MMA: TMEM is held for the load time only, and
@@ -1043,9 +1117,9 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             if ((OSML_TC_COUNTERS && p.counters)) dbg_epi_load += clock64() - dbg_w0 - 0;
                             ptx::tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) ptx::mbar_arrive_cluster_addr(bar_tmem_empty + as * 8);
+                            if (lane0) ptx::mbar_arrive_cluster_addr(bar_tmem_empty + as * 8);
                             released = true;
-                            if (p.debug != 2) {
+                            if (OSML_TC_DBG(p) != 2) {
                                 // hot path: one max tree over the 128 raw dot products, one compare against
                                 // thr + min(h), one vote.  (The rows are sorted by h, so min(h) is tight for the whole
                                 // tile and the test rarely fires without a real candidate.)
@@ -1085,13 +1159,13 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                                 if (last) {
                                     ptx::tc_fence_before();
                                     __syncwarp();
-                                    if (lane == 0) ptx::mbar_arrive_cluster_addr(bar_tmem_empty + as * 8);
+                                    if (lane0) ptx::mbar_arrive_cluster_addr(bar_tmem_empty + as * 8);
                                     released = true;
                                 }
-                                if (p.debug != 2) list.template scan<true>(va, row_base + c, ha, nullptr, h_base + hs + c * 4);
+                                if (OSML_TC_DBG(p) != 2) list.template scan<true>(va, row_base + c, ha, nullptr, h_base + hs + c * 4);
                                 else if (va[0] + va[31] == 12345.678f) list.thr = va[0];
                                 if (!last) ptx::tmem_ld_32x32(taddr + c + 64, va);
-                                if (p.debug != 2) list.template scan<true>(vb, row_base + c + 32, hb, nullptr, h_base + hs + (c + 32) * 4);
+                                if (OSML_TC_DBG(p) != 2) list.template scan<true>(vb, row_base + c + 32, hb, nullptr, h_base + hs + (c + 32) * 4);
                                 else if (vb[0] + vb[31] == 12345.678f) list.thr = vb[0];
                                 if (!last) ptx::tmem_ld_32x32(taddr + c + 96, vb);
                             }
@@ -1100,10 +1174,10 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     if (!released) {
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive_cluster_addr(bar_tmem_empty + as * 8);
+                        if (lane0) ptx::mbar_arrive_cluster_addr(bar_tmem_empty + as * 8);
                     }
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_addr(bar_h_empty + hslot * 8);
+                    if (lane0) ptx::mbar_arrive_addr(bar_h_empty + hslot * 8);
                     if (++hslot == (uint32_t)kTcHSlots) { hslot = 0; hphase ^= 1; }
                 }
                 list.flush();
@@ -1400,6 +1474,7 @@ struct TensorLaunch {
     int opt_cta_group = 0;   // 0 = auto, 1 = single CTA per item, 2 = CTA pairs (cta_group::2)
     int opt_active = 0;      // 0 = auto (= K'), else list entries in use per slot (experiments)
     int opt_precision = 0;   // 0 = auto (bf16, fp16 once a call needed many second passes), 1 = bf16, 2 = fp16
+    int opt_wide_pair = 1;   // 0 = rows too wide for the resident-tile pair kernel go to the single-CTA kernel (A/B)
     int debug = 0;
     int counters = 0;        // 1 = the CTA-pair kernel records where its issuer / epilogue warps wait (printed to stderr)
     // host work to issue once the first block's kernels are queued (the pipelined osml_knn_predict uploads the rest of
@@ -1600,7 +1675,12 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     const size_t pair_extra = (size_t)kTcHSlots * kTcHBlock * 4 + 256 + (size_t)kprime * epi_warps * 32 * 4;
     const bool pair_fits = (size_t)st.smem_optin >=
         (size_t)(st.dp / kTcKB) * kTcABlockBytes + 2 * pair_stage + (size_t)kTcBufCap * 8 * 32 * 8 + pair_extra + 1280;
-    const int tc_cta_group = (reg_lists && tl.opt_cta_group != 1 && pair_fits) ? 2 : 1;
+    // rows too wide for that run the same kernel with a K-block granular ring (kWide): query block + train half block per
+    // stage, at least three stages
+    const size_t wide_stage = (size_t)kTcABlockBytes + kTcBHalfBytes;
+    const bool wide_fits = (size_t)st.smem_optin >= 3 * wide_stage + (size_t)kTcBufCap * 8 * 32 * 8 + pair_extra + 1280;
+    const bool pair_wide = reg_lists && tl.opt_cta_group != 1 && !pair_fits && wide_fits && tl.opt_wide_pair != 0;
+    const int tc_cta_group = (reg_lists && tl.opt_cta_group != 1 && (pair_fits || pair_wide)) ? 2 : 1;
     const int64_t qtile = (int64_t)kTcBM * tc_cta_group;
     const int64_t qpad = (q + qtile - 1) / qtile * qtile;
     const int nqt = (int)(qpad / kTcBM);
@@ -1637,10 +1717,12 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
 
     const size_t list_bytes = reg_lists ? (size_t)kTcBufCap * epi_warps * 32 * 8 : (size_t)kprime * epi_warps * 32 * 8;
     // the query tile stays resident when it leaves room for at least two ring stages; wide rows stream it instead
-    const bool a_resident = tc_cta_group == 2 ||
-        (size_t)st.smem_optin >= (size_t)nkb * kTcABlockBytes + list_bytes + 2 * (size_t)kTcBStageBytes + 1280;
+    const bool a_resident = (tc_cta_group == 2 && !pair_wide) ||
+        (tc_cta_group == 1 &&
+         (size_t)st.smem_optin >= (size_t)nkb * kTcABlockBytes + list_bytes + 2 * (size_t)kTcBStageBytes + 1280);
     const size_t a_bytes = a_resident ? (size_t)nkb * kTcABlockBytes : 0;
-    const size_t stage_bytes = tc_cta_group == 2 ? (size_t)nkb * kTcBHalfBytes
+    const size_t stage_bytes = pair_wide ? wide_stage
+                               : tc_cta_group == 2 ? (size_t)nkb * kTcBHalfBytes
                                : (a_resident ? (size_t)kTcBStageBytes : (size_t)kTcABlockBytes + kTcBStageBytes);
     const size_t extra = tc_cta_group == 2 ? pair_extra : 0;
     const size_t fixed = a_bytes + list_bytes + extra + 256 + 1024;
@@ -1674,7 +1756,7 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     p.cand_val = sc.cand_val.as<float>(); p.cand_idx = sc.cand_idx.as<int>();
     p.cand_thr = sc.cand_thr.as<float>();
     p.h = st.half_norm.as<float>(); p.hmin8 = st.hmin8.as<float>(); p.hblk = st.hblk.as<float>();
-    p.debug = tl.debug;
+    p.debug = OSML_TC_DEBUG ? tl.debug : 0;
     p.counters = tl.counters;
     p.dbg = nullptr;
     if (tl.counters) {
@@ -1683,7 +1765,8 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
         p.dbg = st.dbg.as<unsigned long long>();
     }
     auto kernel = !reg_lists ? knn_tc_filter_kernel<0> : (kprime == 16 ? knn_tc_filter_kernel<16> : knn_tc_filter_kernel<32>);
-    if (tc_cta_group == 2) kernel = kprime == 16 ? knn_tc_filter_pair_kernel<16> : knn_tc_filter_pair_kernel<32>;
+    if (tc_cta_group == 2 && pair_wide) kernel = kprime == 16 ? knn_tc_filter_pair_kernel<16, true> : knn_tc_filter_pair_kernel<32, true>;
+    else if (tc_cta_group == 2) kernel = kprime == 16 ? knn_tc_filter_pair_kernel<16, false> : knn_tc_filter_pair_kernel<32, false>;
     TC_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nitems = nq_single + (nq_units - nq_single) * nseg;
     const int grid = tc_cta_group * std::min(nitems, st.sm_count / tc_cta_group);
@@ -1717,7 +1800,7 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
                 100.0 * h[11] / std::max(1ull, h[4]), (double)h[11] / std::max(1ull, h[12]),
                 (double)(h[4] - h[9] - h[11]) / std::max(1ull, h[6] - h[10] - h[12]));
     }
-    if (tl.debug) return 0;   // profiling ablations: results are meaningless, skip rescoring
+    if (OSML_TC_DEBUG && tl.debug) return 0;   // profiling ablations: results are meaningless, skip rescoring
 
     TcBounds b;
     b.et_max = st.et_max; b.tnorm_max = st.tnorm_max; b.inv_scale = 1.0 / (double)st.scale;
@@ -1727,8 +1810,8 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     b.gamma = (double)(d + 4) * 1.1920928955078125e-07;                      // (D + 4) * 2^-23
     const bool wide_k3 = nslot * kprime > kTcMaxCand;
     const int k3_warps = wide_k3 ? kRescoreWarpsRetry : kRescoreWarps;
-    (wide_k3 ? knn_rescore_kernel<kTcMaxCandRetry, kRescoreWarpsRetry, X> : knn_rescore_kernel<kTcMaxCand, kRescoreWarps, X>)
-        <<<(unsigned)((q + k3_warps - 1) / k3_warps), 32 * k3_warps, 0, stream>>>(
+    auto k3 = wide_k3 ? knn_rescore_kernel<kTcMaxCandRetry, kRescoreWarpsRetry, X> : knn_rescore_kernel<kTcMaxCand, kRescoreWarps, X>;
+    k3<<<(unsigned)((q + k3_warps - 1) / k3_warps), 32 * k3_warps, 0, stream>>>(
         static_cast<const X*>(tl.train), tl.n, d_queries, d, tl.sum_order, q, ksel, sc.cand_val.as<float>(),
         sc.cand_idx.as<int>(), sc.cand_thr.as<float>(), st.perm.as<int>(), st.npad, nslot,
         (int64_t)nq_single * kTcBM * tc_cta_group, halves, kprime, sc.q_norm2.as<double>(), sc.q_err.as<double>(), b, tl.index_base, out_d,
@@ -1812,7 +1895,7 @@ inline int tc_neighbours_block(TensorState& st, const TensorLaunch& tl, const X*
     int rc = tc_begin_unproven_list(st, level, q, stream, err);
     if (rc) return rc;
     rc = tc_filter_block<X>(st, tl, d_queries, q, out_d, out_i, stream, launches, err, level, 0);
-    if (rc || tl.debug) return rc;
+    if (rc || (OSML_TC_DEBUG && tl.debug)) return rc;
     return tc_resolve_unproven<X>(st, tl, d_queries, q, out_d, out_i, stream, fallback, launches, err, direct, level);
 }
 
@@ -1857,7 +1940,7 @@ inline int tensor_neighbours_typed(TensorState& st, const TensorLaunch& tl, cons
         rc = tc_filter_block<X>(st, tl, dq + q0 * tl.d, qb, od + q0 * ksel, out_i + q0 * ksel, stream, launches, err, 0, q0);
         if (rc) return rc;
     }
-    if (tl.debug) return 0;
+    if (OSML_TC_DEBUG && tl.debug) return 0;
     return tc_resolve_unproven<X>(st, tl, dq, q, od, out_i, stream, fallback, launches, err, direct, 0);
 }
 
