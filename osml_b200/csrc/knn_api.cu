@@ -77,6 +77,65 @@ __global__ void transpose_colmajor_kernel(const W* __restrict__ in, W* __restric
     }
 }
 
+// ---- integer matrices on the tensor filter ----------------------------------------------------------------------------
+// numpy evaluates sqrt(sum(square(t - q))) of an integer matrix in the matrix's own type: subtract and square wrap, the
+// sum widens to (u)int64 (osml/predict.py:742).  While no subtraction, square or partial sum can wrap
+// -- |t - q| <= L for every pair of values, L from the type and the feature count -- every intermediate is a small
+// integer, and float64 arithmetic reproduces it EXACTLY (integers below 2^53, whatever the order of the adds): the
+// float64 tensor path (K0 + K1 + K3) then returns the integer oracle's bits, sqrt(float64(sum)).  So an integer index
+// keeps a float64 shadow of its rows for that path; queries are converted per call, and a query that takes some
+// |t - q| beyond L is flagged for the exact direct kernel (which reproduces the wrap-around).
+template <typename T>
+__global__ void int_minmax_kernel(const T* __restrict__ x, int64_t total, double* __restrict__ lo_hi) {
+    double lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)x[i];
+        lo = fmin(lo, v); hi = fmax(hi, v);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if ((threadIdx.x & 31) == 0) {          // doubles of either sign: order-preserving map to unsigned for atomicMin/Max
+        auto key = [](double v) { unsigned long long u = (unsigned long long)__double_as_longlong(v);
+                                  return (u >> 63) ? ~u : (u | 0x8000000000000000ull); };
+        atomicMin(reinterpret_cast<unsigned long long*>(lo_hi), key(lo));
+        atomicMax(reinterpret_cast<unsigned long long*>(lo_hi) + 1, key(hi));
+    }
+}
+
+template <typename T>
+__global__ void int_to_f64_kernel(const T* __restrict__ x, int64_t total, double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (double)x[i];
+}
+
+// one warp per query row: float64 copy + "outside the no-wrap range" flag
+template <typename T>
+__global__ void int_queries_to_f64_kernel(const T* __restrict__ x, int64_t q, int d, double train_lo, double train_hi,
+                                          double limit, double* __restrict__ out, unsigned char* __restrict__ force) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= q) return;
+    double lo = train_lo, hi = train_hi;
+    for (int j = lane; j < d; j += 32) {
+        const double v = (double)x[row * d + j];
+        out[row * d + j] = v;
+        lo = fmin(lo, v); hi = fmax(hi, v);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if (lane == 0) force[row] = (hi - lo <= limit) ? 0 : 1;
+}
+
+template <typename T>
+__global__ void f64_to_int_kernel(const double* __restrict__ x, int64_t total, T* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (T)x[i];                    // integer-valued by construction (int_queries_to_f64_kernel)
+}
+
 }  // namespace
 
 struct osml_knn_index {
@@ -118,6 +177,10 @@ struct osml_knn_index {
     DeviceBuffer part_d, part_i;   // K2 partial lists
     DeviceBuffer nn_d, nn_i;       // final lists
     DeviceBuffer pred;
+    DeviceBuffer train_f64;    // integer dtypes: float64 shadow of the rows for the tensor path (built on first use)
+    DeviceBuffer q_f64, q_force, q_back;   // ... per call: converted queries, direct-kernel flags, rows converted back for K2
+    double int_lo = 0.0, int_hi = 0.0, int_limit = -1.0;   // value range of the train set; largest |t - q| that cannot wrap
+    bool int_tensor_ok = false;
     DeviceBuffer q_shift, q_denom;   // fused query transform (osml_knn_set_query_transform), index dtype
     bool has_q_transform = false, has_q_denom = false;
     osml::TensorState tensor;  // K0/K1/K3 state (bf16 copy, norms, tensor maps, scratch)
@@ -319,9 +382,15 @@ int launch_direct(osml_knn_index* ix, const void* d_queries, int64_t q, void* ou
     }
 }
 
+bool is_int_dtype(int dtype) { return dtype != OSML_KNN_F32 && dtype != OSML_KNN_F64; }
+
+// dtype the tensor path computes in: the matrix's own for floats, float64 (an exact shadow) for integers
+int tensor_dtype(const osml_knn_index* ix) { return is_int_dtype(ix->dtype) ? (int)OSML_KNN_F64 : ix->dtype; }
+
 bool use_tensor_path(const osml_knn_index* ix, int64_t q) {
     if (ix->path == OSML_KNN_PATH_DIRECT) return false;
-    if (!osml::tensor_path_supported(ix->dtype, ix->n, ix->d, ix->k)) return false;
+    if (is_int_dtype(ix->dtype) && !ix->int_tensor_ok) return false;
+    if (!osml::tensor_path_supported(tensor_dtype(ix), ix->n, ix->d, ix->k)) return false;
     if (ix->path == OSML_KNN_PATH_TENSOR) return true;
     // auto.  Measured on a fitted index (tools/crossover.py, profiles/r1h_crossover.jsonl): once K0 has run, the filter
     // beats the direct kernel for every call on the grid, from 20 000 x 32 rows / 32 queries (0.147 vs 0.159 ms) to
@@ -333,6 +402,80 @@ bool use_tensor_path(const osml_knn_index* ix, int64_t q) {
     return ix->tensor.ready || q + ix->seen_queries >= 128;
 }
 
+// ---- integer matrices: float64 shadow for the tensor path --------------------------------------------------------------
+template <typename F>
+int dispatch_int(int dtype, F&& f) {
+    switch (dtype) {
+        case OSML_KNN_I8: return f(int8_t{});
+        case OSML_KNN_I16: return f(int16_t{});
+        case OSML_KNN_I32: return f(int32_t{});
+        case OSML_KNN_I64: return f(int64_t{});
+        case OSML_KNN_U8: return f(uint8_t{});
+        case OSML_KNN_U16: return f(uint16_t{});
+        case OSML_KNN_U32: return f(uint32_t{});
+        case OSML_KNN_U64: return f(uint64_t{});
+        default: return fail(OSML_KNN_EUNSUPPORTED, "not an integer dtype");
+    }
+}
+
+// largest |t - q| for which numpy's subtract and square cannot wrap in the element type
+double int_type_limit(int dtype) {
+    switch (dtype) {
+        case OSML_KNN_I8: return 11.0;             // 11^2 = 121 <= 127
+        case OSML_KNN_I16: return 181.0;           // 181^2 = 32761 <= 32767
+        case OSML_KNN_I32: return 46340.0;         // 46340^2 <= 2^31 - 1
+        case OSML_KNN_I64: return 3037000499.0;    // floor(sqrt(2^63 - 1))
+        case OSML_KNN_U8: return 15.0;             // (t - q) wraps mod 2^8 when t < q, but its square mod 2^8 is (t - q)^2
+        case OSML_KNN_U16: return 255.0;           //   as long as that is below 2^b
+        case OSML_KNN_U32: return 65535.0;
+        case OSML_KNN_U64: return 4294967295.0;
+        default: return -1.0;
+    }
+}
+
+// value range of an integer train matrix (at create) and whether the tensor path can serve it
+int int_scan_train(osml_knn_index* ix) {
+    DeviceBuffer lo_hi;
+    CUDA_TRY(lo_hi.reserve(16));
+    const unsigned long long init[2] = {~0ull, 0ull};
+    CUDA_TRY(cudaMemcpyAsync(lo_hi.ptr, init, 16, cudaMemcpyHostToDevice, ix->stream));
+    const int64_t total = ix->n * ix->d;
+    int rc = dispatch_int(ix->dtype, [&](auto tag) {
+        using T = decltype(tag);
+        int_minmax_kernel<T><<<148 * 8, 256, 0, ix->stream>>>(ix->train.as<T>(), total, lo_hi.as<double>());
+        return (int)OSML_KNN_OK;
+    });
+    if (rc != OSML_KNN_OK) return rc;
+    ix->stats.kernel_launches++;
+    unsigned long long keys[2];
+    CUDA_TRY(cudaMemcpyAsync(keys, lo_hi.ptr, 16, cudaMemcpyDeviceToHost, ix->stream));
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    lo_hi.release();
+    auto unkey = [](unsigned long long u) { u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u; double v; std::memcpy(&v, &u, 8); return v; };
+    ix->int_lo = unkey(keys[0]); ix->int_hi = unkey(keys[1]);
+    // float64 reproduces the integer arithmetic while every partial sum stays below 2^53: d * L^2 <= 2^53
+    const double exact = std::floor(std::sqrt(9007199254740992.0 / (double)ix->d));
+    ix->int_limit = std::min(int_type_limit(ix->dtype), exact);
+    ix->int_tensor_ok = std::fabs(ix->int_lo) <= 9007199254740992.0 && std::fabs(ix->int_hi) <= 9007199254740992.0 &&
+                        ix->int_hi - ix->int_lo <= ix->int_limit;
+    return OSML_KNN_OK;
+}
+
+int int_ensure_shadow(osml_knn_index* ix, cudaStream_t stream) {
+    if (ix->train_f64.ptr) return OSML_KNN_OK;
+    const int64_t total = ix->n * ix->d;
+    CUDA_TRY(ix->train_f64.reserve((size_t)total * 8));
+    int rc = dispatch_int(ix->dtype, [&](auto tag) {
+        using T = decltype(tag);
+        int_to_f64_kernel<T><<<148 * 8, 256, 0, stream>>>(ix->train.as<T>(), total, ix->train_f64.as<double>());
+        return (int)OSML_KNN_OK;
+    });
+    ix->stats.kernel_launches++;
+    if (rc != OSML_KNN_OK) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return OSML_KNN_OK;
+}
+
 // neighbour search into (out_d, out_i): final ascending lists, global indices
 int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d, int64_t* out_i,
                cudaStream_t stream) {
@@ -342,6 +485,25 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
     if (use_tensor_path(ix, q)) {
         osml::TensorLaunch tl;
         tl.train = ix->train.ptr; tl.dtype = ix->dtype; tl.n = ix->n; tl.d = ix->d; tl.k = ix->k;
+        const bool ints = is_int_dtype(ix->dtype);
+        if (ints) {                       // float64 shadow rows, float64 copy of the queries, per-query range flags
+            int rc0 = int_ensure_shadow(ix, stream);
+            if (rc0 != OSML_KNN_OK) return rc0;
+            CUDA_TRY(ix->q_f64.reserve((size_t)q * ix->d * 8));
+            CUDA_TRY(ix->q_force.reserve((size_t)q));
+            rc0 = dispatch_int(ix->dtype, [&](auto tag) {
+                using T = decltype(tag);
+                int_queries_to_f64_kernel<T><<<(unsigned)((q * 32 + 255) / 256), 256, 0, stream>>>(
+                    static_cast<const T*>(d_queries), q, (int)ix->d, ix->int_lo, ix->int_hi, ix->int_limit,
+                    ix->q_f64.as<double>(), ix->q_force.as<unsigned char>());
+                return (int)OSML_KNN_OK;
+            });
+            if (rc0 != OSML_KNN_OK) return rc0;
+            ix->stats.kernel_launches++;
+            CUDA_TRY(cudaGetLastError());
+            tl.train = ix->train_f64.ptr; tl.dtype = OSML_KNN_F64; tl.q_force = ix->q_force.as<unsigned char>();
+            d_queries = ix->q_f64.ptr;
+        }
         tl.sum_order = ix->sum_order; tl.index_base = ix->index_base; tl.slack = ix->slack;
         tl.opt_epi_warps = ix->opt_epi_warps; tl.opt_nseg = ix->opt_nseg; tl.debug = ix->debug; tl.counters = ix->counters;
         tl.opt_smem_lists = ix->opt_smem_lists; tl.opt_cta_group = ix->opt_cta_group; tl.opt_active = ix->opt_active; tl.opt_precision = ix->opt_precision; tl.opt_wide_pair = ix->opt_wide_pair;
@@ -350,7 +512,20 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         std::string err;
         int rc = osml::tensor_neighbours(ix->tensor, tl, d_queries, q, out_d, out_i, stream, &fallback, &launches, &err,
                                          [&](const void* dq, int64_t qq, void* od, int64_t* oi) {
-                                             return launch_direct(ix, dq, qq, od, oi, stream);
+                                             if (!ints) return launch_direct(ix, dq, qq, od, oi, stream);
+                                             // the exact kernel works on the matrix's own type: integer-valued
+                                             // float64 rows back to it
+                                             const int64_t total = qq * ix->d;
+                                             CUDA_TRY(ix->q_back.reserve((size_t)total * dtype_size(ix->dtype)));
+                                             int rcb = dispatch_int(ix->dtype, [&](auto tag) {
+                                                 using T = decltype(tag);
+                                                 f64_to_int_kernel<T><<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+                                                     static_cast<const double*>(dq), total, ix->q_back.as<T>());
+                                                 return (int)OSML_KNN_OK;
+                                             });
+                                             if (rcb != OSML_KNN_OK) return rcb;
+                                             ix->stats.kernel_launches++;
+                                             return launch_direct(ix, ix->q_back.ptr, qq, od, oi, stream);
                                          });
         ix->stats.kernel_launches += launches;
         if (rc != OSML_KNN_OK) return err.empty() ? rc : fail(rc, err);
@@ -461,6 +636,10 @@ int osml_knn_create(osml_knn_index** out, int device, const void* train, int dty
         return cleanup(fail(e == cudaErrorMemoryAllocation ? OSML_KNN_ENOMEM : OSML_KNN_ECUDA, cudaGetErrorString(e)));
     if ((e = cudaStreamSynchronize(ix->stream)) != cudaSuccess) return cleanup(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
     ix->stage.release();
+    if (is_int_dtype(dtype) && osml::tensor_path_supported(OSML_KNN_F64, n, d, k) && n >= 16384) {
+        rc = int_scan_train(ix);          // can the tensor path serve this integer matrix? (value range, see int_type_limit)
+        if (rc != OSML_KNN_OK) return cleanup(rc);
+    }
     *out = ix;
     return OSML_KNN_OK;
 }
@@ -471,6 +650,7 @@ int osml_knn_destroy(osml_knn_index* ix) {
     osml::tensor_release(ix->tensor);
     ix->train.release(); ix->label_bits.release(); ix->stage.release(); ix->queries.release();
     ix->part_d.release(); ix->part_i.release(); ix->nn_d.release(); ix->nn_i.release(); ix->pred.release();
+    ix->train_f64.release(); ix->q_f64.release(); ix->q_force.release(); ix->q_back.release();
     ix->q_shift.release(); ix->q_denom.release();
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
@@ -586,7 +766,7 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
     if (ix->opt_pipeline && wave > 0) {
         if (q >= 2 * wave) qa = wave;
         else if (q >= 4096 && (size_t)q * ix->d * es >= ((size_t)4 << 20)) qa = (q / 2 + 255) / 256 * 256;
-        if (qa < q && !use_tensor_path(ix, std::min(qa, q - qa))) qa = q;
+        if (qa < q && (!use_tensor_path(ix, std::min(qa, q - qa)) || is_int_dtype(ix->dtype))) qa = q;
     }
     const bool pipelined = qa < q;
     CUDA_TRY(cudaEventRecord(ix->ev0, ix->stream));
@@ -811,8 +991,16 @@ int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
     if (key == "path") {
         const int v = (int)value;
         if (v < OSML_KNN_PATH_AUTO || v > OSML_KNN_PATH_TENSOR) return fail(OSML_KNN_EINVAL, "bad path");
-        if (v == OSML_KNN_PATH_TENSOR && !osml::tensor_path_supported(ix->dtype, ix->n, ix->d, ix->k))
-            return fail(OSML_KNN_EUNSUPPORTED, "tensor path needs float32 or float64 data, n >= 256, d <= 8189 and k + 1 + slack <= 64");
+        if (v == OSML_KNN_PATH_TENSOR && is_int_dtype(ix->dtype) && ix->int_limit < 0 &&
+            osml::tensor_path_supported(OSML_KNN_F64, ix->n, ix->d, ix->k)) {
+            DeviceGuard guard(ix->device);            // small integer matrices are not scanned at create
+            int rc = int_scan_train(ix);
+            if (rc != OSML_KNN_OK) return rc;
+        }
+        if (v == OSML_KNN_PATH_TENSOR && (!osml::tensor_path_supported(tensor_dtype(ix), ix->n, ix->d, ix->k) ||
+                                          (is_int_dtype(ix->dtype) && !ix->int_tensor_ok)))
+            return fail(OSML_KNN_EUNSUPPORTED, "tensor path needs n >= 256, d <= 8189, k + 1 + slack <= 64 and float data, or "
+                                               "integer data whose value range cannot wrap in numpy's arithmetic");
         ix->path = v;
         return OSML_KNN_OK;
     }
@@ -840,6 +1028,7 @@ int osml_knn_get_stats(osml_knn_index* ix, osml_knn_stats* out) {
     if (!ix || !out) return fail(OSML_KNN_EINVAL, "null argument");
     ix->stats.device_bytes = (int64_t)(ix->train.cap + ix->label_bits.cap + ix->stage.cap + ix->queries.cap +
                                        ix->part_d.cap + ix->part_i.cap + ix->nn_d.cap + ix->nn_i.cap + ix->pred.cap +
+                                       ix->train_f64.cap + ix->q_f64.cap + ix->q_force.cap + ix->q_back.cap +
                                        osml::tensor_bytes(ix->tensor));
     ix->stats.filter_precision = ix->tensor.ready ? (ix->tensor.f16 ? 2 : 1) : 0;
     *out = ix->stats;

@@ -51,6 +51,13 @@
 #define OSML_TC_DEBUG 0
 #endif
 #define OSML_TC_DBG(p) (OSML_TC_DEBUG ? (p).debug : 0)
+// A/B switches of the K1 epilogue (tools/ab.sh builds variants with -D...)
+#ifndef OSML_TC_LD128
+#define OSML_TC_LD128 0       // 1: the thread's 128 columns in one tcgen05.ld.x128 instead of four .x32
+#endif
+#ifndef OSML_TC_OPAQUE
+#define OSML_TC_OPAQUE 1      // 0: let the compiler re-derive the epilogue's loop invariants per tile
+#endif
 
 namespace osml {
 
@@ -1069,7 +1076,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                                     const_cast<uint32_t*>(&hmin_base), const_cast<uint32_t*>(&taddr0),
                                     const_cast<uint32_t*>(&lane0)};
 #pragma unroll
-                for (uint32_t* r : keep) asm volatile("mov.b32 %0, %0;" : "+r"(*r));
+                for (uint32_t* r : keep) if (OSML_TC_OPAQUE) asm volatile("mov.b32 %0, %0;" : "+r"(*r));
             }
             long long dbg_epi_wait = 0, dbg_epi_drain = 0, dbg_epi_hits = 0, dbg_epi_hit_tiles = 0, dbg_epi_load = 0, dbg_big_cyc = 0, dbg_big_cnt = 0, dbg_mid_cyc = 0, dbg_mid_cnt = 0;
             const long long dbg_e0 = clock64();
@@ -1108,10 +1115,14 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             // accumulator stage goes straight back to the MMA: TMEM is held for the load time only, and
                             // the scan (with its irregular hit handling) gets a full extra tile time of slack
                             float v0[32], v1[32], v2[32], v3[32];
+#if OSML_TC_LD128
+                            ptx::tmem_ld_32x32_x128(taddr, v0, v1, v2, v3);
+#else
                             ptx::tmem_ld_32x32(taddr, v0);
                             ptx::tmem_ld_32x32(taddr + 32, v1);
                             ptx::tmem_ld_32x32(taddr + 64, v2);
                             ptx::tmem_ld_32x32(taddr + 96, v3);
+#endif
                             const float hmin = lds_f32(hmin_base + hs);      // min(h) over the thread's 128 columns
                             ptx::tmem_ld_wait();
                             if ((OSML_TC_COUNTERS && p.counters)) dbg_epi_load += clock64() - dbg_w0 - 0;
@@ -1271,7 +1282,7 @@ knn_rescore_kernel(const X* __restrict__ train, int64_t n, const X* __restrict__
                    const float* __restrict__ cand_thr, const int* __restrict__ perm, int64_t npad, int nslot,
                    int64_t q_single, int slots_single, int kprime, const double* __restrict__ qnorm2,
                    const double* __restrict__ qerr, TcBounds bounds, int64_t index_base, X* __restrict__ out_d,
-                   int64_t* __restrict__ out_i, int* __restrict__ flags) {
+                   int64_t* __restrict__ out_i, int* __restrict__ flags, const unsigned char* __restrict__ force) {
     static_assert(kCand <= 1024, "the per-lane `taken` mask has 32 bits");
     __shared__ float s_acc[kWarps][kCand];
     __shared__ int s_idx[kWarps][kCand];
@@ -1380,6 +1391,7 @@ knn_rescore_kernel(const X* __restrict__ train, int64_t n, const X* __restrict__
         }
     }
     ok = __all_sync(0xffffffffu, ok);
+    if (force != nullptr && force[q]) ok = false;     // the caller knows this query needs the exact direct kernel
     if (lane == 0) flags[q] = ok ? 0 : 1;
 }
 
@@ -1393,11 +1405,13 @@ __global__ void tc_compact_flags_kernel(const int* __restrict__ flags, int64_t q
 
 template <typename X>
 __global__ void tc_gather_rows_kernel(const X* __restrict__ src, const int* __restrict__ list, int count, int d,
-                                      X* __restrict__ dst) {
+                                      X* __restrict__ dst, const unsigned char* __restrict__ force_src,
+                                      unsigned char* __restrict__ force_dst) {
     const int r = blockIdx.x;
     if (r >= count) return;
     const X* s = src + (size_t)list[r] * d;
     for (int j = threadIdx.x; j < d; j += blockDim.x) dst[(size_t)r * d + j] = s[j];
+    if (force_src != nullptr && threadIdx.x == 0) force_dst[r] = force_src[list[r]];
 }
 
 template <typename X>
@@ -1442,14 +1456,14 @@ struct TensorState {
     TcBuffer dbg;
     // per-call scratch; level 0 = the caller's queries, level 1 = the retry of the few queries K3 could not prove
     struct Scratch {
-        TcBuffer q_bf16, q_norm2, q_err, cand_val, cand_idx, cand_thr, flags, fb_list, fb_count, fb_queries, fb_d, fb_i;
+        TcBuffer q_bf16, q_norm2, q_err, cand_val, cand_idx, cand_thr, flags, fb_list, fb_count, fb_queries, fb_d, fb_i, fb_force;
         size_t bytes() const {
             return q_bf16.cap + q_norm2.cap + q_err.cap + cand_val.cap + cand_idx.cap + cand_thr.cap + flags.cap +
-                   fb_list.cap + fb_count.cap + fb_queries.cap + fb_d.cap + fb_i.cap;
+                   fb_list.cap + fb_count.cap + fb_queries.cap + fb_d.cap + fb_i.cap + fb_force.cap;
         }
         void release() {
             for (TcBuffer* b : {&q_bf16, &q_norm2, &q_err, &cand_val, &cand_idx, &cand_thr, &flags, &fb_list, &fb_count,
-                                &fb_queries, &fb_d, &fb_i})
+                                &fb_queries, &fb_d, &fb_i, &fb_force})
                 b->release();
         }
     };
@@ -1481,6 +1495,9 @@ struct TensorLaunch {
     // the queries here, so the copy runs under the first block's K1); 0 = ok, else a status
     const std::function<int()>* before_wait = nullptr;
     int64_t first_block = 0; // > 0: the first block of the call has this many queries (the rest is not on the device yet)
+    // one byte per query of the call (device, nullable): non-zero = this query must go to the exact direct kernel whatever
+    // the completeness proof says (integer matrices: a query outside the range in which numpy's arithmetic cannot wrap)
+    const unsigned char* q_force = nullptr;
 };
 
 using DirectFallback = std::function<int(const void*, int64_t, void*, int64_t*)>;
@@ -1815,7 +1832,7 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
         static_cast<const X*>(tl.train), tl.n, d_queries, d, tl.sum_order, q, ksel, sc.cand_val.as<float>(),
         sc.cand_idx.as<int>(), sc.cand_thr.as<float>(), st.perm.as<int>(), st.npad, nslot,
         (int64_t)nq_single * kTcBM * tc_cta_group, halves, kprime, sc.q_norm2.as<double>(), sc.q_err.as<double>(), b, tl.index_base, out_d,
-        out_i, sc.flags.as<int>());
+        out_i, sc.flags.as<int>(), tl.q_force ? tl.q_force + q_offset : nullptr);
     tc_compact_flags_kernel<<<(unsigned)((q + 255) / 256), 256, 0, stream>>>(sc.flags.as<int>(), q, q_offset,
                                                                              sc.fb_list.as<int>(), sc.fb_count.as<int>());
     *launches += 2;
@@ -1854,8 +1871,10 @@ inline int tc_resolve_unproven(TensorState& st, const TensorLaunch& tl, const X*
         TC_TRY(sc.fb_queries.reserve((size_t)count * d * sizeof(X)));
         TC_TRY(sc.fb_d.reserve((size_t)count * ksel * sizeof(X)));
         TC_TRY(sc.fb_i.reserve((size_t)count * ksel * sizeof(int64_t)));
+        if (tl.q_force) TC_TRY(sc.fb_force.reserve((size_t)count));
         tc_gather_rows_kernel<X><<<count, 128, 0, stream>>>(d_queries, sc.fb_list.as<int>(), count, d,
-                                                            sc.fb_queries.as<X>());
+                                                            sc.fb_queries.as<X>(), tl.q_force,
+                                                            tl.q_force ? sc.fb_force.as<unsigned char>() : nullptr);
         ++*launches;
         if (level == 0) {
             // second chance on the filter: the same kernels over the few unproven queries, cut into as many train
@@ -1863,6 +1882,7 @@ inline int tc_resolve_unproven(TensorState& st, const TensorLaunch& tl, const X*
             // many times deeper and the proof almost always goes through.  Whatever still fails goes to K2 from there.
             TensorLaunch retry = tl;
             retry.opt_nseg = 1 << 20;                  // clamped to the maximum
+            if (tl.q_force) retry.q_force = sc.fb_force.as<unsigned char>();     // follows the gathered queries
             rc = tc_neighbours_block<X>(st, retry, sc.fb_queries.as<X>(), count, sc.fb_d.as<X>(),
                                         sc.fb_i.as<int64_t>(), stream, fallback, launches, err, direct, 1);
             st.retry_queries += count;
