@@ -1,4 +1,7 @@
-"""Ad-hoc device timing of the neighbour-search paths (not the bench): python tools/time_paths.py n d q k path"""
+"""Ad-hoc device timing of the neighbour-search paths (not the bench):
+    python tools/time_paths.py n d q k path [reps] [option=value ...] [dtype=int8 hi=11]
+`dtype` / `hi`: integer data drawn uniformly from 0..hi instead of float32 gaussians (hi = 11 is the widest range int8
+arithmetic cannot wrap in: the integer tensor-filter path)."""
 import sys
 import time
 
@@ -15,9 +18,15 @@ def main():
     reps = int(sys.argv[6]) if len(sys.argv) > 6 else 3
     opts = dict(a.split('=') for a in sys.argv[7:])
     rng = np.random.default_rng(0)
-    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    dtype = np.dtype(opts.pop('dtype', 'float32'))
+    hi = int(opts.pop('hi', 11))
+    if dtype.kind in 'iu':
+        train = np.asfortranarray(rng.integers(0, hi + 1, (n, d)).astype(dtype))
+        test = rng.integers(0, hi + 1, (q, d)).astype(dtype)
+    else:
+        train = np.asfortranarray(rng.standard_normal((n, d)).astype(dtype))
+        test = rng.standard_normal((q, d)).astype(dtype)
     labels = rng.integers(0, 10, n)
-    test = rng.standard_normal((q, d), dtype=np.float32)
     t0 = time.time()
     ix = _native.Index(train, labels, k, 1, 1e-8)
     ix.set_option('path', _native.PATHS[path])
@@ -27,7 +36,7 @@ def main():
     dq = torch.from_numpy(test).cuda()
     out = torch.empty(q, dtype=torch.float64, device='cuda')
     idx = torch.empty((q, k + 1), dtype=torch.int64, device='cuda')
-    dist = torch.empty((q, k + 1), dtype=torch.float32, device='cuda')
+    dist = torch.empty((q, k + 1), dtype=torch.float32 if dtype == np.float32 else torch.float64, device='cuda')
     stream = torch.cuda.current_stream().cuda_stream
     for r in range(reps + 1):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
