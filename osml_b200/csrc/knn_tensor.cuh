@@ -51,13 +51,6 @@
 #define OSML_TC_DEBUG 0
 #endif
 #define OSML_TC_DBG(p) (OSML_TC_DEBUG ? (p).debug : 0)
-// A/B switches of the K1 epilogue (tools/ab.sh builds variants with -D...)
-#ifndef OSML_TC_LD128
-#define OSML_TC_LD128 0       // 1: the thread's 128 columns in one tcgen05.ld.x128 instead of four .x32
-#endif
-#ifndef OSML_TC_OPAQUE
-#define OSML_TC_OPAQUE 1      // 0: let the compiler re-derive the epilogue's loop invariants per tile
-#endif
 
 namespace osml {
 
@@ -79,7 +72,7 @@ struct TcParams {
     int ksteps;          // UMMA K steps (16 bf16 each) actually needed: ceil(d / 16)
     int nqt;             // query tiles
     int nseg;            // train segments
-    int nq_single;       // pair kernel: query-tile pairs swept in one item (see tc_pair_item); the others use nseg
+    int nq_single;       // pair kernel: query-tile pairs swept in one item (see TcItemIter); the others use nseg
     int tiles_per_seg;   // 256-row tiles per segment (segment s owns tiles s, s + nseg, ...: every segment sees the
                          // whole range of row norms, in ascending order)
     int tiles_total;
@@ -823,18 +816,33 @@ constexpr int kTcBHalfBytes = (kTcBN / 2) * 128;      // 16 KB: this CTA's half 
 // Work items of the pair kernel.  Query-tile pairs 0 .. nq_single-1 are swept over the whole train set in ONE item
 // (one warm-up of the candidate lists, the tightest thresholds); the remaining pairs -- those that would leave most of
 // the machine idle in a last partial wave -- are split into nseg interleaved segments (tiles seg, seg + nseg, ...).
-// The split items are numbered segment-major (all pairs' segment 0, then all pairs' segment 1, ...): by the time a
-// later segment of a query starts, its earlier segments have usually finished and their thresholds seed its lists.
-struct TcItem { int qp, seg, nsg; };
-__device__ __forceinline__ TcItem tc_pair_item(const TcParams& p, int item) {
-    TcItem r;
-    if (item < p.nq_single) { r.qp = item; r.seg = 0; r.nsg = 1; }
-    else {
-        const int j = item - p.nq_single, nrest = p.nqt / 2 - p.nq_single;
-        r.qp = p.nq_single + j % nrest; r.seg = j / nrest; r.nsg = p.nseg;
+// Work items of a CTA pair, in the order it processes them (round robin over the item list): the whole-sweep items of
+// pairs 0 .. nq_single-1, then the split pairs' interleaved segments (tiles seg, seg + nseg, ...: every segment sees
+// the whole range of row norms in ascending order), numbered segment-major -- all pairs' segment 0, then all pairs'
+// segment 1, ... -- so that by the time a later segment of a query starts its earlier segments have usually finished
+// and their thresholds seed its lists.  Every item writes candidate slot `slot` of its queries (x halves).
+// (Measured and dropped: cutting the pair-major tile sequence into one contiguous run per CTA pair.  It balances
+// perfectly and makes sweeps as long as possible, but a run in the middle of the norm-sorted order never sees the
+// small-norm rows that settle the thresholds: 10-60 % slower on every shape tried.)
+struct TcItem { int qp, tile0, stride, ntiles, slot; };
+struct TcItemIter {
+    int item, nitems, step;
+    __device__ __forceinline__ TcItemIter(const TcParams& p, int cluster_id, int nclusters) {
+        item = cluster_id; step = nclusters;
+        nitems = p.nq_single + (p.nqt / 2 - p.nq_single) * p.nseg;
     }
-    return r;
-}
+    __device__ __forceinline__ bool next(const TcParams& p, TcItem& r) {
+        if (item >= nitems) return false;
+        if (item < p.nq_single) { r.qp = item; r.tile0 = 0; r.stride = 1; r.slot = 0; }
+        else {
+            const int j = item - p.nq_single, nrest = p.nqt / 2 - p.nq_single;
+            r.qp = p.nq_single + j % nrest; r.slot = j / nrest; r.tile0 = r.slot; r.stride = p.nseg;
+        }
+        r.ntiles = (p.tiles_total - r.tile0 + r.stride - 1) / r.stride;
+        item += step;
+        return true;
+    }
+};
 
 // kWide (rows too long for a resident query tile next to two whole half-tile stages: D > 253): the ring works at K-block
 // granularity instead -- a stage holds [this CTA's 128 x 64 query block][its 128 x 64 half of the train block], one
@@ -867,8 +875,6 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = rank == 0;
-    const int nqp = p.nqt / 2;                    // query-tile pairs (host pads nqt to even)
-    const int nitems = p.nq_single + (nqp - p.nq_single) * p.nseg;
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
@@ -896,11 +902,10 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             if (lane == 0) {
                 // ===== TMA producer (both CTAs): own query tile, own half of each train tile =====
                 uint32_t stage = 0, phase = 0, it = 0, hslot = 0, hphase = 0;
-                for (int item = cluster_id; item < nitems; item += nclusters, ++it) {
-                    const TcItem wi = tc_pair_item(p, item);
-                    const int seg = wi.seg, nsg = wi.nsg, qt = 2 * wi.qp + (int)rank;
-                    const int tile0 = seg;
-                    const int ntiles = (p.tiles_total - seg + nsg - 1) / nsg;
+                TcItemIter items(p, cluster_id, nclusters);
+                for (TcItem wi; items.next(p, wi); ++it) {
+                    const int nsg = wi.stride, qt = 2 * wi.qp + (int)rank;
+                    const int tile0 = wi.tile0, ntiles = wi.ntiles;
                     if (!kWide) {
                         ptx::mbar_wait(a_empty, (it & 1) ^ 1);
                         if (leader) ptx::mbar_expect_tx(a_full, 2u * (uint32_t)p.nkb * kTcABlockBytes);
@@ -950,9 +955,9 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 const uint32_t hi = ptx::umma_desc_hi_k_sw128();
                 const uint32_t ring_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_smem));
                 uint32_t stage = 0, phase = 0, acc_it = 0;
-                for (int item = cluster_id; item < nitems; item += nclusters) {
-                    const TcItem wi = tc_pair_item(p, item);
-                    const int ntiles = (p.tiles_total - wi.seg + wi.nsg - 1) / wi.nsg;
+                TcItemIter items(p, cluster_id, nclusters);
+                for (TcItem wi; items.next(p, wi);) {
+                    const int ntiles = wi.ntiles;
                     for (int t = 0; t < ntiles; ++t, ++acc_it) {
                         const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
                         ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -990,9 +995,9 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 uint32_t stage = 0, phase = 0, it = 0, acc_it = 0;
                 long long dbg_wait_acc = 0, dbg_wait_ops = 0, dbg_issue = 0, dbg_commit = 0, dbg_t2 = 0;
                 const long long dbg_t0 = clock64();
-                for (int item = cluster_id; item < nitems; item += nclusters, ++it) {
-                    const TcItem wi = tc_pair_item(p, item);
-                    const int ntiles = (p.tiles_total - wi.seg + wi.nsg - 1) / wi.nsg;
+                TcItemIter items(p, cluster_id, nclusters);
+                for (TcItem wi; items.next(p, wi); ++it) {
+                    const int ntiles = wi.ntiles;
                     ptx::mbar_wait(a_full, it & 1);
                     ptx::tc_fence_after();
                     for (int t = 0; t < ntiles; ++t, ++acc_it) {
@@ -1076,15 +1081,14 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                                     const_cast<uint32_t*>(&hmin_base), const_cast<uint32_t*>(&taddr0),
                                     const_cast<uint32_t*>(&lane0)};
 #pragma unroll
-                for (uint32_t* r : keep) if (OSML_TC_OPAQUE) asm volatile("mov.b32 %0, %0;" : "+r"(*r));
+                for (uint32_t* r : keep) asm volatile("mov.b32 %0, %0;" : "+r"(*r));
             }
             long long dbg_epi_wait = 0, dbg_epi_drain = 0, dbg_epi_hits = 0, dbg_epi_hit_tiles = 0, dbg_epi_load = 0, dbg_big_cyc = 0, dbg_big_cnt = 0, dbg_mid_cyc = 0, dbg_mid_cnt = 0;
             const long long dbg_e0 = clock64();
-            for (int item = cluster_id; item < nitems; item += nclusters) {
-                const TcItem wi = tc_pair_item(p, item);
-                const int seg = wi.seg, nsg = wi.nsg, qt = 2 * wi.qp + (int)rank;
-                const int tile0 = seg;
-                const int ntiles = (p.tiles_total - seg + nsg - 1) / nsg;
+            TcItemIter items(p, cluster_id, nclusters);
+            for (TcItem wi; items.next(p, wi);) {
+                const int seg = wi.slot, nsg = wi.stride, qt = 2 * wi.qp + (int)rank;
+                const int tile0 = wi.tile0, ntiles = wi.ntiles;
                 // seed the threshold with what earlier segments of the same query already proved: their K'-th best
                 // bounds this query's answer from below, so rows scoring under it cannot matter here either.  The slots
                 // are written by other CTAs of this launch; an unfinished one still reads the NaN bits of the memset in
@@ -1115,14 +1119,10 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             // accumulator stage goes straight back to the MMA: TMEM is held for the load time only, and
                             // the scan (with its irregular hit handling) gets a full extra tile time of slack
                             float v0[32], v1[32], v2[32], v3[32];
-#if OSML_TC_LD128
-                            ptx::tmem_ld_32x32_x128(taddr, v0, v1, v2, v3);
-#else
                             ptx::tmem_ld_32x32(taddr, v0);
                             ptx::tmem_ld_32x32(taddr + 32, v1);
                             ptx::tmem_ld_32x32(taddr + 64, v2);
                             ptx::tmem_ld_32x32(taddr + 96, v3);
-#endif
                             const float hmin = lds_f32(hmin_base + hs);      // min(h) over the thread's 128 columns
                             ptx::tmem_ld_wait();
                             if ((OSML_TC_COUNTERS && p.counters)) dbg_epi_load += clock64() - dbg_w0 - 0;

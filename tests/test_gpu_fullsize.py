@@ -47,17 +47,17 @@ def _full_size_case(n, d, q, k, seed, sample, oracle_sample):
 
 def test_config4_full_size():
     """BASELINE config 4: 1M x 128 fp32 train, 100k queries, k = 10."""
-    _full_size_case(1_000_000, 128, 100_000, 10, seed=4, sample=256, oracle_sample=6)
+    _full_size_case(1_000_000, 128, 100_000, 10, seed=4, sample=2048, oracle_sample=32)
 
 
 def test_config3_full_size():
     """BASELINE config 3: 60k x 784 fp32 train, 10k queries, k = 10."""
-    _full_size_case(60_000, 784, 10_000, 10, seed=3, sample=256, oracle_sample=6)
+    _full_size_case(60_000, 784, 10_000, 10, seed=3, sample=2048, oracle_sample=32)
 
 
 def test_config5_one_shard_full_size():
     """BASELINE config 5, one GPU's share: 2.5M x 96 fp32 rows, k = 32 (a 20k-query sample of the 1M)."""
-    _full_size_case(2_500_000, 96, 20_000, 32, seed=5, sample=128, oracle_sample=3)
+    _full_size_case(2_500_000, 96, 20_000, 32, seed=5, sample=512, oracle_sample=8)
 
 
 def test_adversarial_binary_int8_ties_everywhere():

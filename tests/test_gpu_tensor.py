@@ -474,3 +474,74 @@ def test_auto_path_builds_the_filter_after_128_queries_and_gives_up_on_tie_ridde
     assert all(np.array_equal(a, b) for a, b in zip(first, second))
     parity.assert_matches_oracle(first[0][:40], first[1][:40], first[2][:40], train, labels, test[:40], k, 1,
                                  'classification')
+
+
+# ---- adversarial inputs for the completeness bound ("argued in comments, not tested adversarially") --------
+# The filter's error budget (TcBounds: c_mma, et_max, the 2^-20 tie margin) decides which queries may skip the exact
+# kernel.  Whatever the data does to it, the answer must stay the oracle's: a budget that is too optimistic shows up
+# here as a wrong neighbour, one that is merely conservative as extra fallbacks.
+def test_near_ties_one_ulp_apart_on_a_ray():
+    """Train rows on a ray from the origin, radii one float32 ulp apart: hundreds of rows whose distances to the query
+    differ in the last bit only, far below what a bf16 score can resolve."""
+    rng = np.random.default_rng(21)
+    n, d, k = 20000, 48, 10
+    direction = rng.standard_normal(d)
+    direction /= np.linalg.norm(direction)
+    radii = (1.0 + np.arange(n, dtype=np.float64) * 2.0 ** -23) * 3.0
+    rng.shuffle(radii)
+    train = np.asfortranarray((radii[:, None] * direction[None, :]).astype(np.float32))
+    test = np.concatenate([np.zeros((1, d), np.float32), (rng.standard_normal((40, d)) * 1e-4).astype(np.float32),
+                           (direction[None, :] * radii[:23, None]).astype(np.float32)])
+    labels = rng.integers(0, 4, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+
+
+def test_two_distant_clusters_defeat_the_centring():
+    """Two clusters 2000 apart in every feature: centring leaves +-1000, whose bf16 rounding error (~4 per feature)
+    dwarfs the within-cluster distances (~10).  The bound must notice and send the queries to the exact kernel."""
+    rng = np.random.default_rng(22)
+    n, d, k = 20000, 32, 7
+    side = rng.integers(0, 2, n) * 2.0 - 1.0
+    train = np.asfortranarray((side[:, None] * 1000.0 + rng.standard_normal((n, d))).astype(np.float32))
+    test = ((rng.integers(0, 2, 120) * 2.0 - 1.0)[:, None] * 1000.0 + rng.standard_normal((120, d))).astype(np.float32)
+    labels = rng.standard_normal(n)
+    pred, idx, dist, stats = _run(train, labels, test, k, task='regression')
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'regression')
+
+
+def test_feature_scales_twelve_orders_of_magnitude_apart():
+    rng = np.random.default_rng(23)
+    n, d, k = 30000, 24, 10
+    scale = (10.0 ** rng.uniform(-6, 6, d)).astype(np.float32)
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32) * scale)
+    test = rng.standard_normal((200, d), dtype=np.float32) * scale
+    labels = rng.integers(0, 3, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+
+
+def test_huge_norms_tiny_gaps_float64():
+    """float64 rows of norm ~1e8 whose mutual distances are ~1: the filter copy cannot see any of it."""
+    rng = np.random.default_rng(24)
+    n, d, k = 20000, 16, 5
+    centre = rng.standard_normal(d) * 1e8
+    train = np.asfortranarray(centre[None, :] + rng.standard_normal((n, d)))
+    test = centre[None, :] + rng.standard_normal((64, d))
+    labels = rng.integers(0, 3, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    assert dist.dtype == np.float64
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+
+
+def test_queries_far_outside_the_train_range_and_on_top_of_train_rows():
+    rng = np.random.default_rng(25)
+    n, d, k = 25000, 40, 10
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = np.concatenate([train[:30] * 1.0, train[30:60] + np.float32(1e-6),                  # exact hits, near hits
+                           rng.standard_normal((30, d), dtype=np.float32) * np.float32(1e4),    # far outside
+                           np.full((2, d), 3e37, np.float32)]).astype(np.float32)                # squares overflow to inf
+    labels = rng.integers(0, 5, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    with np.errstate(all='ignore'):
+        parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
