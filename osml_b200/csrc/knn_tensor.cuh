@@ -15,8 +15,9 @@
 //                          The tensor core only computes the D-long dot products (K = D, no padding columns for the
 //                          norms): the hot path compares a max tree over the raw dot products with thr + min(h), and
 //                          only the rare groups of 8 columns that pass subtract h element by element.
-//                            knn_tc_filter_pair_kernel  CTA pairs (cta_group::2), the production kernel for D <= 253
-//                            knn_tc_filter_kernel       one CTA per tile: wide rows, shared-memory lists for k > 21
+//                            knn_tc_filter_pair_kernel  CTA pairs (cta_group::2): resident query tile for D <= 192, a K-block
+//                                                       granular ring (kWide) for wider rows
+//                            knn_tc_filter_kernel       one CTA per tile: shared-memory lists for k > 21
 //   K3  knn_rescore        per query: exact distances of the candidates in the oracle's arithmetic and summation
 //                          order, top-(k+1) by (distance, index), and a completeness proof -- every row the filter
 //                          dropped has score <= the slot's K'-th best, which bounds its true distance from below
@@ -844,7 +845,7 @@ struct TcItemIter {
     }
 };
 
-// kWide (rows too long for a resident query tile next to two whole half-tile stages: D > 253): the ring works at K-block
+// kWide (rows too long for a resident query tile next to two whole half-tile stages: D > 192): the ring works at K-block
 // granularity instead -- a stage holds [this CTA's 128 x 64 query block][its 128 x 64 half of the train block], one
 // barrier round trip per K block, one issuer thread (a tile takes thousands of MMA cycles, its bookkeeping is noise).
 // Everything else -- the CTA pair's M = 256 MMA that halves the L2 -> shared-memory traffic per FLOP of the single-CTA
