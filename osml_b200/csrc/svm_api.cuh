@@ -90,6 +90,9 @@ int svm_decide(osml_svm_machine* m, const void* d_queries, int64_t q, double* d_
         default: e = svm_launch_typed<uint64_t>(m, d_queries, (int)q, &nsplit, stream); break;
     }
     if (e != cudaSuccess) return fail(OSML_KNN_ECUDA, cudaGetErrorString(e));
+    // the launch writes nsplit * q partial sums: never more than was reserved (compute-sanitizer is closed on this pool,
+    // so the bound is checked here)
+    if (nsplit > splits) return fail(OSML_KNN_ECUDA, "internal: decision kernel used more row splits than reserved");
     CUDA_TRY(cudaEventRecord(m->ev1, stream));
     osml::svm_finish_kernel<<<(unsigned)((q + 255) / 256), 256, 0, stream>>>(m->partial.as<double>(), nsplit, (int)q,
                                                                              m->intercept, d_out);
