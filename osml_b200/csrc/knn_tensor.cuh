@@ -1111,7 +1111,8 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     ptx::tc_fence_after();
                     const uint32_t taddr = taddr0 + as * kTcBN;
                     // the tile's h block in shared memory (landed long ago: it was requested with the operand tiles)
-                    ptx::mbar_wait_addr(bar_h_full + hslot * 8, hphase);
+                    // (128-column shares check its barrier under the TMEM load latency instead: -2 % K1 at C4, A/B)
+                    if (cols != 128) ptx::mbar_wait_addr(bar_h_full + hslot * 8, hphase);
                     const uint32_t hs = hslot * (kTcHBlock * 4);
                     bool released = false;
                     if (OSML_TC_DBG(p) != 1 && OSML_TC_DBG(p) != 3) {
@@ -1124,6 +1125,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             ptx::tmem_ld_32x32(taddr + 32, v1);
                             ptx::tmem_ld_32x32(taddr + 64, v2);
                             ptx::tmem_ld_32x32(taddr + 96, v3);
+                            ptx::mbar_wait_addr(bar_h_full + hslot * 8, hphase);     // under the TMEM load latency
                             const float hmin = lds_f32(hmin_base + hs);      // min(h) over the thread's 128 columns
                             ptx::tmem_ld_wait();
                             if ((OSML_TC_COUNTERS && p.counters)) dbg_epi_load += clock64() - dbg_w0 - 0;
@@ -1489,6 +1491,8 @@ struct TensorLaunch {
     int opt_cta_group = 0;   // 0 = auto, 1 = single CTA per item, 2 = CTA pairs (cta_group::2)
     int opt_active = 0;      // 0 = auto (= K'), else list entries in use per slot (experiments)
     int opt_precision = 0;   // 0 = auto (bf16, fp16 once a call needed many second passes), 1 = bf16, 2 = fp16
+    int opt_kprime = 0;      // 0 = auto (tc_kprime), 16 / 32 = list length per slot (experiments: with more segments a slot's
+                             //   share of the true neighbours shrinks; whatever a short list loses, the proof catches)
     int opt_wide_pair = 1;   // 0 = rows too wide for the resident-tile pair kernel go to the single-CTA kernel (A/B)
     int debug = 0;
     int counters = 0;        // 1 = the CTA-pair kernel records where its issuer / epilogue warps wait (printed to stderr)
@@ -1680,7 +1684,7 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     TensorState::Scratch& sc = st.scratch[level];
     const int d = (int)tl.d;
     const int ksel = tl.k + 1;
-    const int kprime = tc_kprime(tl.k, tl.slack);
+    const int kprime = (tl.opt_kprime == 16 || tl.opt_kprime == 32) ? tl.opt_kprime : tc_kprime(tl.k, tl.slack);
     if (kprime > kTcMaxKPrime) { if (err) *err = "k + 1 + slack exceeds 64"; return 4; }
     const bool reg_lists = kprime <= 32 && !tl.opt_smem_lists;
     int epi_warps = reg_lists ? 8 : 4;
