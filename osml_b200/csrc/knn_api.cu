@@ -760,13 +760,20 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
     // Pipelined upload: queries are independent, so a large matrix goes up in two blocks.  The first is one full wave of
     // K1 work items (sm_count x 128 queries: every CTA pair sweeps one tile pair, nothing is split); the rest is copied on
     // a second stream once the first block's kernels are queued, i.e. under its K1, instead of in front of everything.
-    // Smaller calls whose upload is worth hiding (4 MB and more) go up in two halves: K1 cuts either half into enough train
+    // Smaller calls whose upload is worth hiding go up in two halves: K1 cuts either half into enough train
     // segments to fill the machine, so the split costs a few list warm-ups and hides half of the copy.
     const int64_t wave = (int64_t)ix->sm_count * 128;
     int64_t qa = q;
     if (ix->opt_pipeline && wave > 0) {
         if (q >= 2 * wave) qa = wave;
-        else if (q >= 4096 && (size_t)q * ix->d * es >= ((size_t)4 << 20)) qa = (q / 2 + 255) / 256 * 256;
+        else if (q >= 4096 && (size_t)q * ix->d * es >= ((size_t)4 << 20)) {
+            // ... but only where the copy is a sizeable part of the call: ~40 GB/s up against ~1.2 PFLOP/s of filter.  Two
+            // halves hide half of the copy and pay for it with shorter sweeps (measured at 1M x 128 rows: 12 500 queries
+            // 3.3 ms in halves, 2.8 ms whole; 10 000 x 784 against 60 000 rows: 1.9 ms in halves, 2.0 ms whole)
+            const double copy_ms = (double)q * ix->d * es / 40e6;
+            const double filter_ms = 2.0 * (double)ix->n * ix->d * (double)q / 1.2e12;
+            if (copy_ms >= 0.3 * filter_ms) qa = (q / 2 + 255) / 256 * 256;
+        }
         if (qa < q && (!use_tensor_path(ix, std::min(qa, q - qa)) || is_int_dtype(ix->dtype))) qa = q;
     }
     const bool pipelined = qa < q;
