@@ -48,6 +48,13 @@
 #endif
 // -DOSML_TC_DEBUG=1 keeps the profiling ablations of the K1 kernels (TcParams::debug); the product compiles them out --
 // each test was a constant-bank load and a branch per tile on the epilogue's critical path
+// K3 is bound by the latency of its row gathers (each warp walks its candidate rows in ~400 dependent round trips), so
+// what counts is how many warps are resident: the register budget asks for 10 CTAs of 4 warps per SM (48 registers, a few
+// bytes of spills) and the candidate arrays come in three sizes.  Measured at C3 (interleaved A/B, ms per 10k-query call):
+// 7 CTAs 1.12, 10 CTAs 1.02, 12 CTAs 1.03, 16 CTAs 1.12; the query row in shared memory (one copy per warp) 1.09.
+#ifndef OSML_K3_MIN_CTAS
+#define OSML_K3_MIN_CTAS 10
+#endif
 #ifndef OSML_TC_DEBUG
 #define OSML_TC_DEBUG 0
 #endif
@@ -1279,7 +1286,7 @@ __device__ __forceinline__ unsigned long long tc_score_key(float a, int c) {
 // kCand: candidates per query the shared-memory lists hold; kWarps: queries (= warps) per CTA; X: element type of the
 // train / query matrix (float or double) -- distances come out as X
 template <int kCand, int kWarps, typename X>
-__global__ void __launch_bounds__(32 * kWarps)
+__global__ void __launch_bounds__(32 * kWarps, sizeof(X) == 4 ? OSML_K3_MIN_CTAS : 5)     // (float64 would spill at 48 registers)
 knn_rescore_kernel(const X* __restrict__ train, int64_t n, const X* __restrict__ queries, int d, int sum_order,
                    int64_t q_count, int ksel, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
                    const float* __restrict__ cand_thr, const int* __restrict__ perm, int64_t npad, int nslot,
@@ -1833,6 +1840,8 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     const bool wide_k3 = nslot * kprime > kTcMaxCand;
     const int k3_warps = wide_k3 ? kRescoreWarpsRetry : kRescoreWarps;
     auto k3 = wide_k3 ? knn_rescore_kernel<kTcMaxCandRetry, kRescoreWarpsRetry, X> : knn_rescore_kernel<kTcMaxCand, kRescoreWarps, X>;
+    if (!wide_k3 && nslot * kprime <= 128) k3 = knn_rescore_kernel<128, kRescoreWarps, X>;    // less shared memory: more CTAs per SM
+    else if (!wide_k3 && nslot * kprime <= 256) k3 = knn_rescore_kernel<256, kRescoreWarps, X>;
     k3<<<(unsigned)((q + k3_warps - 1) / k3_warps), 32 * k3_warps, 0, stream>>>(
         static_cast<const X*>(tl.train), tl.n, d_queries, d, tl.sum_order, q, ksel, sc.cand_val.as<float>(),
         sc.cand_idx.as<int>(), sc.cand_thr.as<float>(), st.perm.as<int>(), st.npad, nslot,
