@@ -418,7 +418,7 @@ def run_ours(args):
         ctx.close()
         return 0
 
-    kernel = 'knn_tc_filter_pair_kernel<16>' if d <= 253 else 'knn_tc_filter_wide_kernel<16>'
+    kernel = 'knn_tc_filter_pair_kernel<16, resident>' if d <= 192 else 'knn_tc_filter_pair_kernel<16, wide>'
     roofline = tensor_roofline(2.0 * n * d * q * args.steps / max(leg['filt_launches'], 1),
                                leg['filt_ms'] / max(leg['filt_launches'], 1), leg['filt_launches'], total_ms,
                                args.workload, q, kernel, leg['clocks'],
