@@ -1007,7 +1007,7 @@ int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
         }
         if (v == OSML_KNN_PATH_TENSOR && (!osml::tensor_path_supported(tensor_dtype(ix), ix->n, ix->d, ix->k) ||
                                           (is_int_dtype(ix->dtype) && !ix->int_tensor_ok)))
-            return fail(OSML_KNN_EUNSUPPORTED, "tensor path needs n >= 256, d <= 8189, k + 1 + slack <= 64 and float data, or "
+            return fail(OSML_KNN_EUNSUPPORTED, "tensor path needs n >= 256 (2048 x segments for k > 47), d <= 8189, k <= 250 and float data, or "
                                                "integer data whose value range cannot wrap in numpy's arithmetic");
         ix->path = v;
         return OSML_KNN_OK;

@@ -1528,11 +1528,31 @@ inline int tc_kprime(int k, int slack) {
     return (need + 7) / 8 * 8;                            // shared-memory lists, one thread per query row
 }
 
+// Larger k (up to 250): register lists of 32 per slot and at least `min_seg` interleaved train segments, so that the
+// 2 * min_seg slots of a query hold k + 1 + slack candidates between them and each slot's share of the true k + 1
+// nearest -- Binomial(k + 1, 1 / (2 * min_seg)) -- fits its list with four standard deviations to spare.  K3 takes up
+// to 512 candidates per query (8 segments) in the first pass.  Returns the list length, or a value above kTcMaxKPrime
+// when the filter cannot serve this k.
+inline int tc_plan_lists(int k, int slack, int* min_seg) {
+    *min_seg = 1;
+    const int kprime = tc_kprime(k, slack);
+    if (kprime <= kTcMaxKPrime) return kprime;
+    if (slack < 0) slack = tc_default_slack(k);
+    const int need = k + 1 + slack;
+    for (int seg = 2; seg <= kTcMaxCand / 64; ++seg) {
+        const double p = 0.5 / seg, mu = (k + 1) * p, sd = std::sqrt((k + 1) * p * (1.0 - p));
+        if (2 * seg * 32 >= need && mu + 4.0 * sd <= 32.0) { *min_seg = seg; return 32; }
+    }
+    return kTcMaxKPrime + 1;
+}
+
 inline bool tensor_path_supported(int dtype, int64_t n, int64_t d, int k) {
     if (dtype != 0 /* OSML_KNN_F32 */ && dtype != 1 /* OSML_KNN_F64 */) return false;
     if (n < 256 || d < 1) return false;
     if (d > 8189) return false;                   // 128 K blocks of 64 bf16
-    return tc_kprime(k, -1) <= kTcMaxKPrime;
+    int min_seg = 1;
+    if (tc_plan_lists(k, -1, &min_seg) > kTcMaxKPrime) return false;
+    return min_seg == 1 || n >= (int64_t)min_seg * 8 * kTcBN;       // a segment is at least 8 tiles long
 }
 
 inline size_t tensor_bytes(const TensorState& s) {
@@ -1691,8 +1711,10 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     TensorState::Scratch& sc = st.scratch[level];
     const int d = (int)tl.d;
     const int ksel = tl.k + 1;
-    const int kprime = (tl.opt_kprime == 16 || tl.opt_kprime == 32) ? tl.opt_kprime : tc_kprime(tl.k, tl.slack);
-    if (kprime > kTcMaxKPrime) { if (err) *err = "k + 1 + slack exceeds 64"; return 4; }
+    int min_seg = 1;
+    const int planned = tc_plan_lists(tl.k, tl.slack, &min_seg);
+    const int kprime = (tl.opt_kprime == 16 || tl.opt_kprime == 32) ? tl.opt_kprime : planned;
+    if (kprime > kTcMaxKPrime) { if (err) *err = "k + 1 + slack is beyond what the filter's lists hold"; return 4; }
     const bool reg_lists = kprime <= 32 && !tl.opt_smem_lists;
     int epi_warps = reg_lists ? 8 : 4;
     if (tl.opt_epi_warps == 4 || (tl.opt_epi_warps == 8 && (reg_lists || kprime <= 24))) epi_warps = tl.opt_epi_warps;
@@ -1729,13 +1751,16 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     const int units = std::max(1, st.sm_count / tc_cta_group);
     const int nq_units = nqt / tc_cta_group;                 // query tiles (single CTA) or tile pairs
     int nseg = 1, nq_single = 0;
+    if (max_seg < min_seg) { if (err) *err = "too few training rows for the segments this k needs"; return 4; }
     if (tl.opt_nseg > 0) {
-        nseg = std::min(tl.opt_nseg, max_seg);
+        nseg = std::max(min_seg, std::min(tl.opt_nseg, max_seg));
     } else {
-        const int rem = tc_cta_group == 2 ? nq_units % units : nq_units;     // units of work left for the split part
+        // (large k: every pair is split, a whole-sweep item would have two slots only)
+        const int rem = (tc_cta_group == 2 && min_seg == 1) ? nq_units % units : nq_units;     // units of work left for the split part
         nq_single = nq_units - rem;
+        nseg = min_seg;
         double best = 1e30;
-        for (int cand = 1; cand <= max_seg && rem > 0; ++cand) {
+        for (int cand = min_seg; cand <= max_seg && rem > 0; ++cand) {
             const double cost = std::ceil((double)rem * cand / units) / cand + 0.01 * (cand - 1);
             if (cost < best - 1e-9) { best = cost; nseg = cand; }
         }

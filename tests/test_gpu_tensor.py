@@ -545,3 +545,33 @@ def test_queries_far_outside_the_train_range_and_on_top_of_train_rows():
     pred, idx, dist, stats = _run(train, labels, test, k)
     with np.errstate(all='ignore'):
         parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+
+
+@pytest.mark.parametrize('k,n,d', [(64, 40000, 24), (100, 50000, 32), (250, 60000, 16)])
+def test_large_k_runs_on_the_filter_with_forced_segments(k, n, d):
+    """k beyond what two lists of 32 per query hold: register lists of 32 per slot and enough interleaved train segments
+    that the slots hold k + 1 + slack candidates between them (tc_plan_lists).  Same bits as the oracle; the direct
+    kernel sees next to nothing."""
+    rng = np.random.default_rng(k)
+    q = 300
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = rng.standard_normal((q, d), dtype=np.float32)
+    labels = rng.integers(0, 6, n)
+    pred, idx, dist, stats = _run(train, labels, test, k)
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'classification')
+    assert stats['tensor_queries'] == q and stats['fallback_queries'] <= q // 10, stats
+
+
+def test_k_beyond_the_filter_stays_on_the_direct_kernel():
+    rng = np.random.default_rng(77)
+    n, d, k = 30000, 8, 300
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    labels = rng.standard_normal(n)
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    with pytest.raises(NotImplementedError):
+        ix.set_option('path', _native.PATH_TENSOR)
+    test = rng.standard_normal((40, d), dtype=np.float32)
+    pred, idx, dist = ix.predict(test, _native.REGRESSION, return_neighbours=True)
+    assert ix.stats()['tensor_queries'] == 0
+    ix.close()
+    parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'regression')
