@@ -160,6 +160,8 @@ struct osml_knn_index {
     int opt_active = 0;
     int opt_precision = 0;
     int opt_wide_pair = 1;
+    int opt_hot = 0;
+    int opt_live = 1;
     int opt_kprime = 0;
     int debug = 0;
     int counters = 0;
@@ -507,7 +509,7 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         }
         tl.sum_order = ix->sum_order; tl.index_base = ix->index_base; tl.slack = ix->slack;
         tl.opt_epi_warps = ix->opt_epi_warps; tl.opt_nseg = ix->opt_nseg; tl.debug = ix->debug; tl.counters = ix->counters;
-        tl.opt_smem_lists = ix->opt_smem_lists; tl.opt_cta_group = ix->opt_cta_group; tl.opt_active = ix->opt_active; tl.opt_precision = ix->opt_precision; tl.opt_wide_pair = ix->opt_wide_pair; tl.opt_kprime = ix->opt_kprime;
+        tl.opt_smem_lists = ix->opt_smem_lists; tl.opt_cta_group = ix->opt_cta_group; tl.opt_active = ix->opt_active; tl.opt_precision = ix->opt_precision; tl.opt_wide_pair = ix->opt_wide_pair; tl.opt_kprime = ix->opt_kprime; tl.opt_hot = ix->opt_hot; tl.opt_live = ix->opt_live;
         tl.before_wait = ix->before_wait; tl.first_block = ix->first_block;
         int64_t fallback = 0, launches = 0;
         std::string err;
@@ -1028,6 +1030,8 @@ int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
     }
     if (key == "kprime") { ix->opt_kprime = (int)value; return OSML_KNN_OK; }
     if (key == "wide_pair") { ix->opt_wide_pair = (int)value; return OSML_KNN_OK; }
+    if (key == "hot") { ix->opt_hot = (int)value; return OSML_KNN_OK; }
+    if (key == "live") { ix->opt_live = (int)value; return OSML_KNN_OK; }
     if (key == "query_block") { ix->query_block = (int64_t)value; return OSML_KNN_OK; }
     if (key == "pipeline") { ix->opt_pipeline = value != 0.0; return OSML_KNN_OK; }
     return fail(OSML_KNN_EINVAL, "unknown option: " + key);

@@ -95,6 +95,10 @@ struct TcParams {
     float* cand_val;     // [qpad][nslot][kprime]
     int* cand_idx;
     float* cand_thr;     // [qpad][nslot]: every row the slot dropped has score <= this (-inf: nothing dropped)
+    int nhot;            // pair kernel, split items: segments 0 .. nhot-1 interleave over tiles [0, thot) (the small-norm rows,
+    int thot;            //    where the neighbours are); the others are contiguous runs of what follows (see TcItemIter)
+    unsigned int* gate;  // [qpad] pair kernel, split items: the best list threshold any slot of the query has proven so far,
+                         //    order-preserving bits (tc_gate_enc); 0 = none yet
     const float* h;      // [npad] 0.5*|t^|^2 (+inf for padding rows)
     const float* hmin8;  // [npad / 8] minimum of h over each group of 8 rows
     const float* hblk;   // [tiles][288]: the same per 256-row tile, h then the 32 group minima (pair kernel, bulk copies)
@@ -363,6 +367,27 @@ __device__ __forceinline__ float tc_list_min(const float (&lv)[KP]) {
 // predicated 8-byte store each), and the warp then flushes the buffers into the lists in rounds -- round r inserts
 // entry r of every lane that has one.  Everything dropped anywhere is <= the list minimum at that time <= the final
 // threshold.
+// Live gate of a query (pair kernel, queries whose sweep is split over several items): every slot publishes its list
+// threshold -- K' rows of the query score above it -- and drops whatever scores at or below the best threshold ANY slot of
+// the query has published.  K3's proof already asks lower(thr) > d_(k+1) of every slot, i.e. of the largest threshold, so a
+// slot that drops up to that largest threshold loses nothing the proof could have used; it just stops inserting rows
+// that cannot matter.  Any stale value is a valid gate (thresholds only grow), so relaxed accesses do.
+__device__ __forceinline__ uint32_t tc_gate_enc(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float tc_gate_dec(uint32_t u) {        // 0 (nothing published) decodes to a NaN, which fmaxf ignores
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+__device__ __forceinline__ uint32_t tc_gate_load(const unsigned int* addr) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tc_gate_publish(unsigned int* addr, float thr) {
+    asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(addr), "r"(tc_gate_enc(thr)) : "memory");
+}
+
 constexpr int kTcHSlots = 8;          // ring of per-tile h blocks in the pair kernel
 constexpr int kTcBufCap = 16;         // buffered candidates per thread; a flush is forced above kTcBufCap - 8
 
@@ -386,7 +411,9 @@ struct TcRegList {
     float lv[KP];
     int lr[kSmemRows ? 1 : KP];
     uint32_t rows_addr, rows_stride;   // kSmemRows: shared address of this thread's entry 0, bytes between entries
-    float thr;
+    float thr;             // the list's own minimum
+    float gate;            // best threshold another slot of the same query has proven (-inf: none)
+    float eff;             // max(thr, gate): what a score must beat to matter
     uint32_t buf_addr;     // shared-memory address of this thread's buffer entry 0
     uint32_t buf_stride;   // bytes between consecutive entries of one thread (= epilogue threads * 8)
     int cnt;               // buffered candidates
@@ -407,8 +434,14 @@ struct TcRegList {
             else lr[e] = -1;
         }
         thr = tc_list_min<KP>(lv);
+        gate = -INFINITY;
+        eff = thr;
         cnt = 0;
         rd = 0;
+    }
+    __device__ __forceinline__ void raise_gate(float g) {     // NaN (nothing published yet) leaves it as it is
+        gate = fmaxf(gate, g);
+        eff = fmaxf(thr, gate);
     }
     // branch-free insert (a select per entry): lanes with take == false match no slot
     __device__ __forceinline__ void insert_sel(bool take, float cur, int row) {
@@ -433,6 +466,7 @@ struct TcRegList {
             }
         }
         thr = tc_list_min<KP>(lv);
+        eff = fmaxf(thr, gate);
     }
     __device__ __forceinline__ int row_of(int e) const {
         return kSmemRows ? (int)__float_as_uint(lds_f32(rows_addr + (uint32_t)e * rows_stride)) : lr[kSmemRows ? 0 : e];
@@ -445,7 +479,7 @@ struct TcRegList {
         if (have) lds_v2(buf_addr + (uint32_t)rd * buf_stride, vb, rb);
         rd += have ? 1 : 0;
         const float val = __uint_as_float(vb);
-        const bool take = val > thr;
+        const bool take = val > eff;
         if (__any_sync(0xffffffffu, take)) insert_sel(take, val, (int)rb);
         if (!__any_sync(0xffffffffu, rd < cnt)) { cnt = 0; rd = 0; }    // linear buffers: rewind once all are drained
     }
@@ -467,7 +501,7 @@ struct TcRegList {
                 "{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p st.shared.v2.b32 [%0], {%1, %3};\n\t"
                 "@p add.u32 %0, %0, %4;\n\t}"
                 : "+r"(waddr)
-                : "f"(w), "f"(thr), "r"(row0 + j), "r"(buf_stride)
+                : "f"(w), "f"(eff), "r"(row0 + j), "r"(buf_stride)
                 : "memory");
         }
         cnt = (int)((waddr - buf_addr) >> buf_shift);
@@ -480,7 +514,7 @@ struct TcRegList {
         const float g1 = tc_max8(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
         const float g2 = tc_max8(v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23]);
         const float g3 = tc_max8(v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]);
-        const bool p0 = g0 > thr + hm.x, p1 = g1 > thr + hm.y, p2 = g2 > thr + hm.z, p3 = g3 > thr + hm.w;
+        const bool p0 = g0 > eff + hm.x, p1 = g1 > eff + hm.y, p2 = g2 > eff + hm.z, p3 = g3 > eff + hm.w;
         uint32_t m = 0;
         if (__any_sync(0xffffffffu, p0 | p1 | p2 | p3)) {
             m = (__any_sync(0xffffffffu, p0) ? 1u : 0u) | (__any_sync(0xffffffffu, p1) ? 2u : 0u) |
@@ -495,8 +529,8 @@ struct TcRegList {
         const float g1 = tc_max8(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
         const float g2 = tc_max8(v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23]);
         const float g3 = tc_max8(v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]);
-        return (g0 > thr + hm.x ? 1u : 0u) | (g1 > thr + hm.y ? 2u : 0u) | (g2 > thr + hm.z ? 4u : 0u) |
-               (g3 > thr + hm.w ? 8u : 0u);
+        return (g0 > eff + hm.x ? 1u : 0u) | (g1 > eff + hm.y ? 2u : 0u) | (g2 > eff + hm.z ? 4u : 0u) |
+               (g3 > eff + hm.w ? 8u : 0u);
     }
     // slow path over the chunks held in registers; `mask` has one bit per group of 8 columns of v0 | v1 | v2 | v3;
     // h of column 0 of v0 is at hrow (global memory) or, with kSmemH, at shared-memory address h_saddr
@@ -690,7 +724,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int tile0 = seg;                                   // segments interleave: tiles seg, seg + nseg, ...
                 const int ntiles = (p.tiles_total - seg + p.nseg - 1) / p.nseg;
                 list.reset();
-                if (OSML_TC_DBG(p) == 4) list.thr = INFINITY;   // ablation: fast path only
+                if (OSML_TC_DBG(p) == 4) list.thr = list.eff = INFINITY;   // ablation: fast path only
                 for (int t = 0; t < ntiles; ++t, ++acc_it) {
                     const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
                     ptx::mbar_wait(&tmem_full[as], aphase);
@@ -829,6 +863,11 @@ constexpr int kTcBHalfBytes = (kTcBN / 2) * 128;      // 16 KB: this CTA's half 
 // the whole range of row norms in ascending order), numbered segment-major -- all pairs' segment 0, then all pairs'
 // segment 1, ... -- so that by the time a later segment of a query starts its earlier segments have usually finished
 // and their thresholds seed its lists.  Every item writes candidate slot `slot` of its queries (x halves).
+// Hot-first split (nhot < nseg): the filter copy is sorted by row norm and score = q.t - h, so the rows that end up in a
+// query's lists sit overwhelmingly in the first tiles.  Interleaving ALL segments hands every item its own share of
+// those rows, i.e. its own dense list warm-up.  Instead the segments that make up the first wave of items interleave
+// over the first thot tiles only, and the later ones take contiguous runs of the rest: by the time they start the
+// query's gate (see tc_gate_enc) is settled and almost nothing they see passes it.
 // (Measured and dropped: cutting the pair-major tile sequence into one contiguous run per CTA pair.  It balances
 // perfectly and makes sweeps as long as possible, but a run in the middle of the norm-sorted order never sees the
 // small-norm rows that settle the thresholds: 10-60 % slower on every shape tried.)
@@ -841,12 +880,19 @@ struct TcItemIter {
     }
     __device__ __forceinline__ bool next(const TcParams& p, TcItem& r) {
         if (item >= nitems) return false;
-        if (item < p.nq_single) { r.qp = item; r.tile0 = 0; r.stride = 1; r.slot = 0; }
+        if (item < p.nq_single) { r.qp = item; r.tile0 = 0; r.stride = 1; r.slot = 0; r.ntiles = p.tiles_total; }
         else {
             const int j = item - p.nq_single, nrest = p.nqt / 2 - p.nq_single;
-            r.qp = p.nq_single + j % nrest; r.slot = j / nrest; r.tile0 = r.slot; r.stride = p.nseg;
+            r.qp = p.nq_single + j % nrest; r.slot = j / nrest;
+            if (r.slot < p.nhot) {                     // hot segments interleave over the first thot tiles
+                r.tile0 = r.slot; r.stride = p.nhot;
+                r.ntiles = (p.thot - r.tile0 + p.nhot - 1) / p.nhot;
+            } else {                                   // the others: contiguous, equal runs of the remaining tiles
+                const long long c = r.slot - p.nhot, ncold = p.nseg - p.nhot, rest = p.tiles_total - p.thot;
+                const int lo = p.thot + (int)(rest * c / ncold), hi = p.thot + (int)(rest * (c + 1) / ncold);
+                r.tile0 = lo; r.stride = 1; r.ntiles = hi - lo;
+            }
         }
-        r.ntiles = (p.tiles_total - r.tile0 + r.stride - 1) / r.stride;
         item += step;
         return true;
     }
@@ -1097,21 +1143,26 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             for (TcItem wi; items.next(p, wi);) {
                 const int seg = wi.slot, nsg = wi.stride, qt = 2 * wi.qp + (int)rank;
                 const int tile0 = wi.tile0, ntiles = wi.ntiles;
-                // seed the threshold with what earlier segments of the same query already proved: their K'-th best
-                // bounds this query's answer from below, so rows scoring under it cannot matter here either.  The slots
-                // are written by other CTAs of this launch; an unfinished one still reads the NaN bits of the memset in
-                // front of the launch, which fmaxf ignores.
+                // A split query starts from the best threshold the other slots of the same query have proven so far (its
+                // gate, see tc_gate_enc) and keeps following it, one relaxed load per tile, issued in front of the wait
+                // for the accumulator; its own threshold is published whenever it has grown.
                 const size_t q = (size_t)qt * kTcBM + m;
-                float seed = -INFINITY;
-                for (int s2 = 0; s2 < seg; ++s2)
-                    seed = fmaxf(seed, *(const volatile float*)(p.cand_thr + q * p.nslot + (size_t)s2 * halves + half));
-                list.reset(seed, p.kactive);
-                if (OSML_TC_DBG(p) == 4) list.thr = INFINITY;       // ablation: fast path only
+                const bool live = p.gate != nullptr && (nsg > 1 || (p.nseg > 1 && wi.qp >= p.nq_single));       // warp-uniform
+                unsigned int* const gate_addr = p.gate + q;
+                list.reset(-INFINITY, p.kactive);
+                if (live) list.raise_gate(tc_gate_dec(tc_gate_load(gate_addr)));
+                float published = list.gate;
+                if (OSML_TC_DBG(p) == 4) list.thr = list.eff = INFINITY;       // ablation: fast path only
                 int row_base = tile0 * kTcBN + half * cols;
                 for (int t = 0; t < ntiles; ++t, ++acc_it, row_base += nsg * kTcBN) {
                     const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
                     // list maintenance rides on the wait for the next accumulator tile
                     const long long dbg_w0 = (OSML_TC_COUNTERS && p.counters) ? clock64() : 0;
+                    uint32_t gate_bits = 0;
+                    if (live) {
+                        if (list.thr > published) { tc_gate_publish(gate_addr, list.thr); published = list.thr; }
+                        gate_bits = tc_gate_load(gate_addr);
+                    }
                     while (!__all_sync(0xffffffffu, ptx::mbar_try_wait_addr(bar_tmem_full + as * 8, aphase)))
                         if (list.pending()) list.flush_round();
                     if ((OSML_TC_COUNTERS && p.counters)) dbg_epi_wait += clock64() - dbg_w0;
@@ -1135,6 +1186,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             ptx::mbar_wait_addr(bar_h_full + hslot * 8, hphase);     // under the TMEM load latency
                             const float hmin = lds_f32(hmin_base + hs);      // min(h) over the thread's 128 columns
                             ptx::tmem_ld_wait();
+                            if (live) list.raise_gate(tc_gate_dec(gate_bits));
                             if ((OSML_TC_COUNTERS && p.counters)) dbg_epi_load += clock64() - dbg_w0 - 0;
                             ptx::tc_fence_before();
                             __syncwarp();
@@ -1146,7 +1198,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                                 // tile and the test rarely fires without a real candidate.)
                                 const float m0 = tc_max32(v0), m1 = tc_max32(v1), m2 = tc_max32(v2), m3 = tc_max32(v3);
                                 const float tile_max = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                                const float bar = list.thr + hmin;
+                                const float bar = list.eff + hmin;
                                 if (__any_sync(0xffffffffu, tile_max > bar)) {
                                     // which 32-column chunks (warp-uniform), then which groups of 8 inside those only
                                     const uint32_t cmask = __reduce_or_sync(0xffffffffu, (m0 > bar ? 1u : 0u) | (m1 > bar ? 2u : 0u) |
@@ -1173,6 +1225,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             float va[32], vb[32];
                             ptx::tmem_ld_32x32(taddr, va);
                             ptx::tmem_ld_32x32(taddr + 32, vb);
+                            if (live) list.raise_gate(tc_gate_dec(gate_bits));
                             for (int c = 0; c < cols; c += 64) {
                                 const float4 ha = lds_f4(hm_base + hs + (c >> 1)), hb = lds_f4(hm_base + hs + (c >> 1) + 16);
                                 ptx::tmem_ld_wait();
@@ -1208,8 +1261,10 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 int filled = 0;
     #pragma unroll
                 for (int e = 0; e < KP; ++e) { const int r = list.row_of(e); ov[e] = list.lv[e]; oi[e] = r; filled += r >= 0 ? 1 : 0; }
-                // everything this slot dropped scores <= thr (placeholders keep thr at the seed while the list is not full)
-                p.cand_thr[q * p.nslot + slot] = (filled >= p.kactive || seed > -INFINITY) ? list.thr : -INFINITY;
+                // everything this slot dropped scores <= its own threshold (once the list is full) or <= the last gate it used
+                const float bound = fmaxf(filled >= p.kactive ? list.thr : -INFINITY, list.gate);
+                p.cand_thr[q * p.nslot + slot] = bound;
+                if (live && filled >= p.kactive && list.thr > published) tc_gate_publish(gate_addr, list.thr);
             }
             if ((OSML_TC_COUNTERS && p.counters) && lane == 0) {
                 atomicAdd(p.dbg + 3, (unsigned long long)dbg_epi_wait);
@@ -1272,17 +1327,81 @@ __device__ __forceinline__ double tc_exact_distance(const double* __restrict__ t
     return exact_distance<double>(t, q, d, sum_order);
 }
 
+// Exact distances of the candidate rows work[j0 .. j1) in numpy's left-to-right order (sum_order == 1), FOUR LANES PER
+// ROW.  With a lane per row every 16-byte load of a warp touches one cache line per lane, and K3 is bound by those L1
+// wavefronts (47 M per call at 10 000 x 784, profiles/r2_c3_k1_k3_ncu.md).  Here a lane loads 32 contiguous bytes of its
+// row per trip, the four lanes of a group 128: a quarter of the wavefronts per row.  The sum stays ONE sequential chain
+// per row, exactly the oracle's: the partial sum travels lane 0 -> 1 -> 2 -> 3 -> lane 0 of the next trip by shuffles,
+// and each lane adds its eight (four for doubles) squared differences in order when the sum is with it.  Rows shorter
+// than a whole trip are padded with zeros, which a sum of squares absorbs exactly (x + 0 == x for x >= +0, NaN, inf).
+// Needs rows that are a whole number of 16-byte pieces; eight rows per pass of the warp.
+template <typename X> struct TcVec16;
+template <> struct TcVec16<float> { using type = float4; };
+template <> struct TcVec16<double> { using type = double2; };
+__device__ __forceinline__ void tc_sq_diffs(const float4 t, const float4 q, float* e) {
+    using E = Elem<float>;
+    e[0] = E::sq_diff(t.x, q.x); e[1] = E::sq_diff(t.y, q.y); e[2] = E::sq_diff(t.z, q.z); e[3] = E::sq_diff(t.w, q.w);
+}
+__device__ __forceinline__ void tc_sq_diffs(const double2 t, const double2 q, double* e) {
+    using E = Elem<double>;
+    e[0] = E::sq_diff(t.x, q.x); e[1] = E::sq_diff(t.y, q.y);
+}
+template <typename X>
+__device__ __forceinline__ void tc_exact_distances_seq4(const X* __restrict__ train, const int* __restrict__ idx,
+                                                        const short* __restrict__ work, int j0, int j1,
+                                                        const X* __restrict__ qrow, int d, X* __restrict__ dist, int lane) {
+    using E = Elem<X>;
+    using V = typename TcVec16<X>::type;
+    constexpr int kPer = 16 / (int)sizeof(X);       // elements per 16-byte piece
+    const int sub = lane & 3, grp = lane >> 2;
+    const int nv = d / kPer;                         // pieces per row
+    const int nfull = nv >> 3;                       // trips in which all four lanes hold two pieces (a group covers 8)
+    const int ntrip = (nv + 7) >> 3;
+    V zero;
+    memset(&zero, 0, sizeof(V));
+    const V* q0 = reinterpret_cast<const V*>(qrow) + sub * 2;
+    const uint32_t src = (uint32_t)((lane & ~3) | ((sub + 3) & 3));      // the lane in front of this one in the chain
+    for (int jb = j0; jb < j1; jb += 8) {
+        const int j = jb + grp;
+        const bool valid = j < j1;                   // idle groups re-read the first row of the pass (same cache lines)
+        const V* tp = reinterpret_cast<const V*>(train + (size_t)idx[work[valid ? j : j0]] * d) + sub * 2;
+        const V* qp = q0;
+        X acc = (X)0;
+        V ta, tb, qa, qb;
+        auto load_checked = [&](int f) {             // the one trip at the end of a row that is not a whole trip long
+            ta = f < nv ? __ldg(tp) : zero; tb = f + 1 < nv ? __ldg(tp + 1) : zero;
+            qa = f < nv ? __ldg(qp) : zero; qb = f + 1 < nv ? __ldg(qp + 1) : zero;
+        };
+        if (nfull > 0) { ta = __ldg(tp); tb = __ldg(tp + 1); qa = __ldg(qp); qb = __ldg(qp + 1); }
+        else load_checked(sub * 2);
+#pragma unroll 1
+        for (int it = 0; it < ntrip; ++it) {
+            X e[2 * kPer];
+            tc_sq_diffs(ta, qa, e);
+            tc_sq_diffs(tb, qb, e + kPer);
+            tp += 8; qp += 8;                        // next trip's pieces are on their way while the chain runs
+            if (it + 1 < nfull) { ta = __ldg(tp); tb = __ldg(tp + 1); qa = __ldg(qp); qb = __ldg(qp + 1); }
+            else if (it + 1 < ntrip) load_checked((it + 1) * 8 + sub * 2);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const X in = __shfl_sync(0xffffffffu, acc, src);
+                if (sub == s) {
+                    X a = in;
+#pragma unroll
+                    for (int i = 0; i < 2 * kPer; ++i) a = E::add(a, e[i]);
+                    acc = a;
+                }
+            }
+        }
+        if (valid && sub == 3) dist[j] = E::finish(acc);
+    }
+}
+
 // One warp per query.  Exact distances are only computed where they can matter: first for the k+1 candidates with the
 // best filter score, whose largest exact distance D0 caps the answer; any other candidate whose score-derived lower
 // bound already exceeds D0 cannot be among the k+1 nearest and is never gathered from HBM.  Work is kept proportional
 // to the candidates that matter (a few dozen) even when many (segment, half) slots feed the query: the k+1 best scores
 // are picked by k+1 warp arg-max rounds, and everything after that runs on compacted lists.
-__device__ __forceinline__ unsigned long long tc_score_key(float a, int c) {
-    uint32_t u = __float_as_uint(a);
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);            // order-preserving map of float to unsigned
-    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)c);   // ties: lowest position
-}
-
 // kCand: candidates per query the shared-memory lists hold; kWarps: queries (= warps) per CTA; X: element type of the
 // train / query matrix (float or double) -- distances come out as X
 template <int kCand, int kWarps, typename X>
@@ -1293,7 +1412,6 @@ knn_rescore_kernel(const X* __restrict__ train, int64_t n, const X* __restrict__
                    int64_t q_single, int slots_single, int kprime, const double* __restrict__ qnorm2,
                    const double* __restrict__ qerr, TcBounds bounds, int64_t index_base, X* __restrict__ out_d,
                    int64_t* __restrict__ out_i, int* __restrict__ flags, const unsigned char* __restrict__ force) {
-    static_assert(kCand <= 1024, "the per-lane `taken` mask has 32 bits");
     __shared__ float s_acc[kWarps][kCand];
     __shared__ int s_idx[kWarps][kCand];
     __shared__ X s_dist[kWarps][kCand];           // exact distances, by position in s_work
@@ -1321,63 +1439,84 @@ knn_rescore_kernel(const X* __restrict__ train, int64_t n, const X* __restrict__
         return (sqrt(fmax(l2, 0.0)) - (eq + bounds.et_max)) * bounds.inv_scale * (1.0 - bounds.gamma);
     };
 
+    // Selection keys live in registers: the order-preserving bits of the filter score with the candidate number in the
+    // low bits (ties and the dropped score bits only decide WHICH rows are looked at first -- any k+1 exact distances
+    // cap the answer), 0 = empty / already picked.  One warp arg-max is then a register max tree and one REDUX.
+    constexpr int kPerLane = kCand / 32;
+    constexpr uint32_t kIdMask = (uint32_t)kCand - 1u;
+    static_assert((kCand & (kCand - 1)) == 0, "candidate numbers are packed into the low bits of the keys");
+    uint32_t key[kPerLane];
     int nvalid = 0;
-    for (int c = lane; c < ncand; c += 32) {
-        const int pos = ci[c];                        // position in the (norm-sorted) filter copy; negative: empty slot
-        const int row = (pos >= 0 && pos < npad) ? perm[pos] : -1;        // train row; -1 for padding positions
-        const bool valid = row >= 0 && row < n;
-        idx[c] = valid ? row : kIdxSentinel;
-        acc[c] = valid ? cv[c] : -INFINITY;
-        nvalid += valid ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        const int c = lane + 32 * i;
+        key[i] = 0u;
+        if (c < ncand) {
+            const int pos = ci[c];                    // position in the (norm-sorted) filter copy; negative: empty slot
+            const int row = (pos >= 0 && pos < npad) ? perm[pos] : -1;    // train row; -1 for padding positions
+            const bool valid = row >= 0 && row < n;
+            const float score = cv[c];
+            idx[c] = valid ? row : kIdxSentinel;
+            acc[c] = valid ? score : -INFINITY;
+            nvalid += valid ? 1 : 0;
+            if (valid) key[i] = max(tc_gate_enc(score) & ~kIdMask, kIdMask + 1u) | (kIdMask - (uint32_t)c);
+        }
     }
     for (int off = 16; off > 0; off >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, off);
     __syncwarp();
     bool ok = nvalid >= ksel;
-    // pass 1: the k+1 best-scoring candidates, one warp arg-max round each (ncand <= 1024: at most 32 entries per lane)
-    uint32_t taken = 0;                               // bit i: candidate lane + 32 * i already picked
-    const int nsel = min(ksel, nvalid);
+    // rows that are a whole number of 16-byte pieces, summed left to right: four lanes per row (tc_exact_distances_seq4)
+    const bool coop = sum_order == 1 && (d % (16 / (int)sizeof(X))) == 0;
+    // pass 1: the best-scoring candidates -- k+1 of them, or the next multiple of the eight rows a cooperative pass takes
+    const int nsel = min(coop ? ((ksel + 7) & ~7) : ksel, nvalid);
     for (int s = 0; s < nsel; ++s) {
-        unsigned long long best = 0ull;
-        for (int c = lane, i = 0; c < ncand; c += 32, ++i) {
-            if (((taken >> i) & 1u) || idx[c] == kIdxSentinel) continue;
-            const unsigned long long key = tc_score_key(acc[c], c);
-            best = key > best ? key : best;
-        }
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o > best ? o : best;
-        }
-        const int c = (int)(0xFFFFFFFFu - (uint32_t)best);
-        if ((c & 31) == lane) taken |= 1u << (c >> 5);
+        uint32_t mx = key[0];
+#pragma unroll
+        for (int i = 1; i < kPerLane; ++i) mx = max(mx, key[i]);
+        const uint32_t best = __reduce_max_sync(0xffffffffu, mx);
+        const int c = (int)(kIdMask - (best & kIdMask));
+        const int mine = (c & 31) == lane ? (c >> 5) : -1;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) key[i] = i == mine ? 0u : key[i];
+        if (mine >= 0) acc[c] = __int_as_float(0x7fc00000);       // picked (K1 never lists a NaN score: they fail `> thr`)
         if (lane == 0) work[s] = (short)c;
     }
     __syncwarp();
-    X d0 = (X)0;
-    bool d0_nan = false;
+    if (coop) tc_exact_distances_seq4<X>(train, idx, work, 0, nsel, qrow, d, dist, lane);
+    else
+        for (int j = lane; j < nsel; j += 32)
+            dist[j] = tc_exact_distance(train + (size_t)idx[work[j]] * d, qrow, d, sum_order);
+    __syncwarp();
+    // the (k+1)-th smallest of these exact distances caps the answer
     for (int j = lane; j < nsel; j += 32) {
-        const X dc = tc_exact_distance(train + (size_t)idx[work[j]] * d, qrow, d, sum_order);
-        dist[j] = dc;
-        d0 = dc > d0 ? dc : d0;
-        d0_nan = d0_nan || dc != dc;
+        const X dj = dist[j];
+        int rank = 0;
+        for (int o = 0; o < nsel; ++o) rank += key_less(dist[o], o, dj, j) ? 1 : 0;
+        if (rank == ksel - 1) s_best[warp] = dj;
     }
-    for (int off = 16; off > 0; off >>= 1) {
-        const X o = __shfl_xor_sync(0xffffffffu, d0, off);
-        d0 = o > d0 ? o : d0;
-    }
-    d0_nan = __any_sync(0xffffffffu, d0_nan) || !ok;
+    __syncwarp();
+    const X d0 = ok ? s_best[warp] : (X)0;
+    const bool d0_nan = d0 != d0 || !ok;
+    __syncwarp();
     const double cap = d0_nan ? (double)INFINITY : (double)d0 * (1.0 + 9.5367431640625e-07);
     // pass 2: whatever the cap cannot rule out, compacted so that the gathers are spread over the lanes
     int m = nsel;
-    for (int c0 = 0, i = 0; c0 < ncand; c0 += 32, ++i) {
-        const int c = c0 + lane;
-        const bool need = c < ncand && !((taken >> i) & 1u) && idx[c] != kIdxSentinel && !(lower(acc[c]) > cap);
-        const uint32_t ballot = __ballot_sync(0xffffffffu, need);
-        if (need) work[m + __popc(ballot & ((1u << lane) - 1u))] = (short)c;
-        m += __popc(ballot);
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        if (32 * i < ncand) {                         // warp-uniform
+            const int c = 32 * i + lane;
+            const float a = c < ncand ? acc[c] : 0.0f;
+            const bool need = c < ncand && a == a && idx[c] != kIdxSentinel && !(lower(a) > cap);   // valid, not picked in pass 1
+            const uint32_t ballot = __ballot_sync(0xffffffffu, need);
+            if (need) work[m + __popc(ballot & ((1u << lane) - 1u))] = (short)c;
+            m += __popc(ballot);
+        }
     }
     __syncwarp();
-    for (int j = nsel + lane; j < m; j += 32)
-        dist[j] = tc_exact_distance(train + (size_t)idx[work[j]] * d, qrow, d, sum_order);
+    if (coop) tc_exact_distances_seq4<X>(train, idx, work, nsel, m, qrow, d, dist, lane);
+    else
+        for (int j = nsel + lane; j < m; j += 32)
+            dist[j] = tc_exact_distance(train + (size_t)idx[work[j]] * d, qrow, d, sum_order);
     __syncwarp();
     // rank the computed candidates by (distance, index); keys are unique because the slots cover disjoint row sets
     for (int j = lane; j < m; j += 32) {
@@ -1466,13 +1605,13 @@ struct TensorState {
     TcBuffer dbg;
     // per-call scratch; level 0 = the caller's queries, level 1 = the retry of the few queries K3 could not prove
     struct Scratch {
-        TcBuffer q_bf16, q_norm2, q_err, cand_val, cand_idx, cand_thr, flags, fb_list, fb_count, fb_queries, fb_d, fb_i, fb_force;
+        TcBuffer q_bf16, q_norm2, q_err, cand_val, cand_idx, cand_thr, gate, flags, fb_list, fb_count, fb_queries, fb_d, fb_i, fb_force;
         size_t bytes() const {
-            return q_bf16.cap + q_norm2.cap + q_err.cap + cand_val.cap + cand_idx.cap + cand_thr.cap + flags.cap +
+            return q_bf16.cap + q_norm2.cap + q_err.cap + cand_val.cap + cand_idx.cap + cand_thr.cap + gate.cap + flags.cap +
                    fb_list.cap + fb_count.cap + fb_queries.cap + fb_d.cap + fb_i.cap + fb_force.cap;
         }
         void release() {
-            for (TcBuffer* b : {&q_bf16, &q_norm2, &q_err, &cand_val, &cand_idx, &cand_thr, &flags, &fb_list, &fb_count,
+            for (TcBuffer* b : {&q_bf16, &q_norm2, &q_err, &cand_val, &cand_idx, &cand_thr, &gate, &flags, &fb_list, &fb_count,
                                 &fb_queries, &fb_d, &fb_i, &fb_force})
                 b->release();
         }
@@ -1500,6 +1639,9 @@ struct TensorLaunch {
     int opt_precision = 0;   // 0 = auto (bf16, fp16 once a call needed many second passes), 1 = bf16, 2 = fp16
     int opt_kprime = 0;      // 0 = auto (tc_kprime), 16 / 32 = list length per slot (experiments: with more segments a slot's
                              //   share of the true neighbours shrinks; whatever a short list loses, the proof catches)
+    int opt_hot = 0;         // split items: 0 = every segment interleaves; n = the first n segments interleave over the
+                             //   small-norm tiles and the rest take contiguous runs (TcItemIter; experiments)
+    int opt_live = 1;        // 0 = split items neither publish nor follow their query's gate (A/B)
     int opt_wide_pair = 1;   // 0 = rows too wide for the resident-tile pair kernel go to the single-CTA kernel (A/B)
     int debug = 0;
     int counters = 0;        // 1 = the CTA-pair kernel records where its issuer / epilogue warps wait (printed to stderr)
@@ -1768,6 +1910,21 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     }
     const int tiles_per_seg = (tiles_total + nseg - 1) / nseg;
     const int nslot = nseg * halves;
+    // hot-first split (TcItemIter; option `hot` = n): the first n segments interleave over their share of the small-norm
+    // tiles, the later ones take contiguous runs of the rest.  Measured at 10 000 x 784 queries against 60 000 rows with the
+    // two first-wave segments hot: K1 unchanged (0.695 vs 0.692 ms), but the hot slots' thresholds sit so close to the
+    // (k+1)-th neighbour that the proof fails for a few queries per call and the second pass costs 0.2 ms -- so the
+    // default keeps every segment interleaved.  Large k (min_seg > 1) must: each slot needs an equal share of the
+    // true neighbours.
+    int nhot = nseg, thot = tiles_total;
+    if (tc_cta_group == 2 && nseg > 1 && min_seg == 1 && nq_units > nq_single) {
+        int h = tl.opt_hot > 0 ? tl.opt_hot : nseg;      // default: every segment interleaves (see below)
+        h = std::max(1, std::min(h, nseg));
+        if (h < nseg) {
+            nhot = h;
+            thot = std::max(nhot, (int)(((long long)tiles_total * h + nseg / 2) / nseg));
+        }
+    }
 
     const size_t list_bytes = reg_lists ? (size_t)kTcBufCap * epi_warps * 32 * 8 : (size_t)kprime * epi_warps * 32 * 8;
     // the query tile stays resident when it leaves room for at least two ring stages; wide rows stream it instead
@@ -1791,6 +1948,7 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     TC_TRY(sc.cand_val.reserve((size_t)qpad * nslot * kprime * sizeof(float)));
     TC_TRY(sc.cand_idx.reserve((size_t)qpad * nslot * kprime * sizeof(int)));
     TC_TRY(sc.cand_thr.reserve((size_t)qpad * nslot * sizeof(float)));
+    TC_TRY(sc.gate.reserve((size_t)qpad * sizeof(unsigned int)));
     TC_TRY(sc.flags.reserve((size_t)q * sizeof(int)));
 
     const int64_t threads = qpad * 32;
@@ -1809,6 +1967,8 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     p.tiles_total = tiles_total; p.kprime = kprime; p.f16 = st.f16 ? 1 : 0; p.kactive = (tl.opt_active > 0 && tl.opt_active <= kprime) ? tl.opt_active : kprime; p.epi_warps = epi_warps; p.stages = stages; p.nslot = nslot; p.a_resident = a_resident ? 1 : 0;
     p.cand_val = sc.cand_val.as<float>(); p.cand_idx = sc.cand_idx.as<int>();
     p.cand_thr = sc.cand_thr.as<float>();
+    p.nhot = nhot; p.thot = thot;
+    p.gate = (tc_cta_group == 2 && nseg > 1 && tl.opt_live != 0) ? sc.gate.as<unsigned int>() : nullptr;
     p.h = st.half_norm.as<float>(); p.hmin8 = st.hmin8.as<float>(); p.hblk = st.hblk.as<float>();
     p.debug = OSML_TC_DEBUG ? tl.debug : 0;
     p.counters = tl.counters;
@@ -1831,7 +1991,7 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
         TC_TRY(cudaEventCreate(&e1));
         st.ev_k1.push_back(e1);
     }
-    TC_TRY(cudaMemsetAsync(sc.cand_thr.ptr, 0xFF, (size_t)qpad * nslot * sizeof(float), stream));   // NaN bits: "not written"
+    if (p.gate) TC_TRY(cudaMemsetAsync(sc.gate.ptr, 0, (size_t)qpad * sizeof(unsigned int), stream));   // 0: nothing published
     if (level == 0) TC_TRY(cudaEventRecord(st.ev_k1[st.ev_k1_used], stream));
     kernel<<<grid, kTcThreads, smem, stream>>>(map_a, tc_cta_group == 2 ? st.map_b_half : st.map_b, p);
     if (level == 0) { TC_TRY(cudaEventRecord(st.ev_k1[st.ev_k1_used + 1], stream)); st.ev_k1_used += 2; }
