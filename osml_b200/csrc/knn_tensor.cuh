@@ -613,6 +613,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint64_t* tmem_empty = bars + 18;             // [2]
     uint64_t* a_full = bars + 20;
     uint64_t* a_empty = bars + 21;
+    uint64_t* first_done = bars + 22;             // [2]       (wide rows, leader: K block 0 of the tile in this stage is issued)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -922,6 +923,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     uint64_t* tmem_empty = bars + 18;             // [2]       (used in the leader)
     uint64_t* a_full = bars + 20;                 //           (used in the leader)
     uint64_t* a_empty = bars + 21;
+    uint64_t* first_done = bars + 22;             // [2]       (wide rows, leader: K block 0 of the tile in this stage is issued)
     uint64_t* h_full = bars + 24;                 // [kTcHSlots]  this CTA's copy of the tile's h block has landed
     uint64_t* h_empty = bars + 24 + kTcHSlots;    // [kTcHSlots]  ... and every epilogue warp is done with it
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24 + 2 * kTcHSlots);
@@ -937,7 +939,11 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 2 * p.epi_warps); }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tmem_full[s], kWide ? 2 : 1);     // wide rows: one arrival per issuer thread
+            ptx::mbar_init(&tmem_empty[s], 2 * p.epi_warps);
+            ptx::mbar_init(&first_done[s], 1);
+        }
         ptx::mbar_init(a_full, 2);
         ptx::mbar_init(a_empty, 2);
         for (int s = 0; s < kTcHSlots; ++s) { ptx::mbar_init(&h_full[s], 1); ptx::mbar_init(&h_empty[s], p.epi_warps); }
@@ -1002,36 +1008,73 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     }
                 }
             }
-        } else if (kWide && warp == 1) {
+        } else if (kWide && (warp == 1 || warp == 3)) {
             if (lane == 0 && leader) {
-                // ===== MMA issuer (leader CTA only), K-block granular ring =====
+                // ===== MMA issuers (leader CTA only), K-block granular ring =====
+                // Two threads share every tile: K blocks are numbered through the whole run of this CTA pair (they sit in
+                // the ring in that order) and issuer 0 (warp 1) takes the even ones, issuer 1 (warp 3) the odd ones.  The
+                // tensor core takes an MMA when its thread gets to it, so a lone issuer's barrier round trips (a full-wait
+                // and a commit per K block, ~150 cycles against 512 cycles of MMA) were pipe idle time; now one thread waits
+                // and commits while the other's four MMAs run.  Within a tile the order of the K blocks is free (the sum
+                // is the same up to the rounding the error bound already covers) EXCEPT that the block with K block 0
+                // overwrites the accumulator: its issuer signals `first_done` once those MMAs are issued, the other
+                // waits for it before its first block of the tile.  Both commit to tmem_full (two arrivals).
+                const uint32_t issuer = (uint32_t)warp >> 1;
                 const uint32_t idesc = (p.f16 ? ptx::umma_idesc_f16(2 * kTcBM, kTcBN) : ptx::umma_idesc_bf16(2 * kTcBM, kTcBN));
                 const uint32_t hi = ptx::umma_desc_hi_k_sw128();
                 const uint32_t ring_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_smem));
-                uint32_t stage = 0, phase = 0, acc_it = 0;
-                TcItemIter items(p, cluster_id, nclusters);
-                for (TcItem wi; items.next(p, wi);) {
-                    const int ntiles = wi.ntiles;
-                    for (int t = 0; t < ntiles; ++t, ++acc_it) {
-                        const uint32_t as = acc_it & 1, aphase = (acc_it >> 1) & 1;
+                const uint32_t stage_step = stage_bytes >> 4;
+                int ntot = 0;                                    // tiles this CTA pair computes, all items together
+                {
+                    TcItemIter items(p, cluster_id, nclusters);
+                    for (TcItem wi; items.next(p, wi);) ntot += wi.ntiles;
+                }
+                const int nkb = p.nkb, nstages = p.stages;
+                // this thread's next K block: number kb of tile `tile`, sitting in ring stage `stage`
+                int tile = 0, kb = (int)issuer;
+                uint32_t stage = issuer, phase = 0;
+                if (stage >= (uint32_t)nstages) { stage -= nstages; phase ^= 1; }
+                bool enter = true;                               // the next block is this thread's first of its tile
+                long long dbg_wait_acc = 0, dbg_wait_ops = 0;
+                const long long dbg_t0 = clock64();
+                while (tile < ntot) {
+                    const uint32_t as = (uint32_t)tile & 1, aphase = ((uint32_t)tile >> 1) & 1;
+                    const uint32_t tmem_d = tmem_base + as * kTcBN;
+                    if (enter) {
+                        const long long dbg_a0 = (OSML_TC_COUNTERS && p.counters) ? clock64() : 0;
                         ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
-                        const uint32_t tmem_d = tmem_base + as * kTcBN;
-                        for (int kb = 0; kb < p.nkb; ++kb) {
-                            ptx::mbar_wait(&full_bar[stage], phase);
-                            ptx::tc_fence_after();
-                            const int nks = p.ksteps - kb * 4;
-                            const uint32_t a_lo = ring_lo0 + stage * (stage_bytes >> 4);
-                            const uint32_t b_lo = a_lo + (kTcABlockBytes >> 4);
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                if (ks < nks)
-                                    ptx::umma_bf16_ss_pair_lohi(tmem_d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc,
-                                                                (uint32_t)((kb | ks) != 0));
-                            ptx::umma_commit_pair(&empty_bar[stage]);      // both CTAs may refill this stage
-                            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
-                        }
-                        ptx::umma_commit_pair(&tmem_full[as]);             // both CTAs' epilogues may read the tile
+                        if (kb != 0) ptx::mbar_wait(&first_done[as], aphase);      // K block 0 has been issued
+                        if ((OSML_TC_COUNTERS && p.counters)) dbg_wait_acc += clock64() - dbg_a0;
+                        enter = false;
                     }
+                    const long long dbg_o0 = (OSML_TC_COUNTERS && p.counters) ? clock64() : 0;
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    if ((OSML_TC_COUNTERS && p.counters)) dbg_wait_ops += clock64() - dbg_o0;
+                    ptx::tc_fence_after();
+                    const int nks = p.ksteps - kb * 4;
+                    const uint32_t a_lo = ring_lo0 + stage * stage_step;
+                    const uint32_t b_lo = a_lo + (kTcABlockBytes >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        if (ks < nks)
+                            ptx::umma_bf16_ss_pair_lohi(tmem_d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc,
+                                                        (uint32_t)((kb | ks) != 0));
+                    ptx::umma_commit_pair(&empty_bar[stage]);      // both CTAs may refill this stage
+                    if (kb == 0) {
+                        ptx::tc_fence_before();
+                        ptx::mbar_arrive(&first_done[as]);
+                    }
+                    kb += 2; stage += 2;
+                    if (stage >= (uint32_t)nstages) { stage -= nstages; phase ^= 1; }
+                    if (kb >= nkb) {                               // that was this thread's last block of the tile
+                        ptx::umma_commit_pair(&tmem_full[as]);     // one of the two arrivals the epilogues wait for
+                        kb -= nkb; ++tile; enter = true;
+                    }
+                }
+                if ((OSML_TC_COUNTERS && p.counters) && issuer == 0) {
+                    atomicAdd(p.dbg + 0, (unsigned long long)dbg_wait_acc);
+                    atomicAdd(p.dbg + 1, (unsigned long long)dbg_wait_ops);
+                    atomicAdd(p.dbg + 2, (unsigned long long)(clock64() - dbg_t0));
                 }
             }
         } else if (!kWide && (warp == 1 || warp == 3)) {
