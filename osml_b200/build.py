@@ -13,7 +13,7 @@ OUT = os.path.join(HERE, 'libosml_knn.so')
 SOURCES = ['knn_api.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-pthread', '-shared']
 
 
 def _nvcc():

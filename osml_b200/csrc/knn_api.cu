@@ -16,6 +16,7 @@
 #include "knn_direct.cuh"
 #include "knn_tensor.cuh"
 #include "knn_transform.cuh"
+#include "host_stager.cuh"
 
 namespace {
 
@@ -167,9 +168,11 @@ struct osml_knn_index {
     int counters = 0;
     int64_t query_block = 0;
     int opt_pipeline = 1;      // osml_knn_predict: 1 = upload the tail of a large query matrix under the first block's K1
+    int opt_stager = 1;        // pageable host matrices of 2 MB and more go up through the pinned staging ring (host_stager.cuh)
+    int opt_pipeline_blocks = 0;   // equal blocks of a call below two waves: 0 = two (more: experiments)
     int sm_count = 0;
-    const std::function<int()>* before_wait = nullptr;   // both set only while a pipelined osml_knn_predict is in flight
-    int64_t first_block = 0;
+    const std::function<int(int)>* before_block = nullptr;   // both set only while a pipelined osml_knn_predict is in flight
+    std::vector<int64_t> block_ends;
     int64_t seen_queries = 0;  // since create: auto builds the filter once enough queries have been asked for
     bool auto_direct = false;  // auto: the filter could not prove most queries of a call, stay on the direct kernel
 
@@ -206,26 +209,47 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-int upload_matrix(osml_knn_index* ix, const void* host, int layout, int64_t rows, int64_t cols, DeviceBuffer& dst,
-                  cudaStream_t stream) {
-    const size_t es = dtype_size(ix->dtype);
-    const size_t bytes = (size_t)rows * cols * es;
-    CUDA_TRY(dst.reserve(bytes));
-    if (layout == OSML_KNN_ROW_MAJOR || rows == 1 || cols == 1) {
-        CUDA_TRY(cudaMemcpyAsync(dst.ptr, host, bytes, cudaMemcpyHostToDevice, stream));
-        return OSML_KNN_OK;
+// Pageable host memory goes through the pinned staging ring (host_stager.cuh) from 2 MB up: chunks of about a megabyte,
+// gathered by a few threads, one cudaMemcpyAsync each.  `dev` receives `bytes` contiguous bytes; piece `i` of them comes
+// from host address src(i_offset) -- contiguous for row-major input, one column segment after the other otherwise.
+int staged_copy_rowmajor(osml_knn_index* ix, const char* host, char* dev, size_t bytes, cudaStream_t stream) {
+    std::vector<osml::HostStager::Chunk> chunks;
+    for (size_t off = 0; off < bytes; off += osml::HostStager::kSlotBytes) {
+        const size_t nb = std::min(osml::HostStager::kSlotBytes, bytes - off);
+        const char* src = host + off;
+        chunks.push_back({dev + off, nb, [src, nb](char* slot) { memcpy(slot, src, nb); }});
     }
-    CUDA_TRY(ix->stage.reserve(bytes));
-    CUDA_TRY(cudaMemcpyAsync(ix->stage.ptr, host, bytes, cudaMemcpyHostToDevice, stream));
-    dim3 block(32, 8), grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
-    switch (es) {
-        case 1: transpose_colmajor_kernel<uint8_t><<<grid, block, 0, stream>>>(ix->stage.as<uint8_t>(), dst.as<uint8_t>(), rows, cols); break;
-        case 2: transpose_colmajor_kernel<uint16_t><<<grid, block, 0, stream>>>(ix->stage.as<uint16_t>(), dst.as<uint16_t>(), rows, cols); break;
-        case 4: transpose_colmajor_kernel<uint32_t><<<grid, block, 0, stream>>>(ix->stage.as<uint32_t>(), dst.as<uint32_t>(), rows, cols); break;
-        default: transpose_colmajor_kernel<uint64_t><<<grid, block, 0, stream>>>(ix->stage.as<uint64_t>(), dst.as<uint64_t>(), rows, cols); break;
+    CUDA_TRY(osml::HostStager::instance().copy(ix->device, chunks, stream));
+    return OSML_KNN_OK;
+}
+
+// column-major host matrix, rows [r0, r1) -> device staging region [cols][nr] (element (i, j) at j * nr + i)
+int staged_copy_colmajor(osml_knn_index* ix, const char* host, int64_t rows, int64_t cols, int64_t r0, int64_t r1,
+                         size_t es, char* dev, cudaStream_t stream) {
+    const int64_t nr = r1 - r0;
+    const size_t col_bytes = (size_t)nr * es, slot = osml::HostStager::kSlotBytes;
+    std::vector<osml::HostStager::Chunk> chunks;
+    if (col_bytes <= slot) {                         // whole column segments, as many as fit a slot
+        const int64_t per = std::max<int64_t>(1, (int64_t)(slot / col_bytes));
+        for (int64_t j0 = 0; j0 < cols; j0 += per) {
+            const int64_t j1 = std::min(cols, j0 + per);
+            const char* src = host + ((size_t)j0 * rows + r0) * es;
+            const size_t stride = (size_t)rows * es;
+            chunks.push_back({dev + (size_t)j0 * col_bytes, (size_t)(j1 - j0) * col_bytes,
+                              [src, stride, col_bytes, j0, j1](char* out) {
+                                  for (int64_t j = j0; j < j1; ++j)
+                                      memcpy(out + (size_t)(j - j0) * col_bytes, src + (size_t)(j - j0) * stride, col_bytes);
+                              }});
+        }
+    } else {                                         // long columns: pieces of one column
+        for (int64_t j = 0; j < cols; ++j)
+            for (size_t off = 0; off < col_bytes; off += slot) {
+                const size_t nb = std::min(slot, col_bytes - off);
+                const char* src = host + ((size_t)j * rows + r0) * es + off;
+                chunks.push_back({dev + (size_t)j * col_bytes + off, nb, [src, nb](char* out) { memcpy(out, src, nb); }});
+            }
     }
-    ix->stats.kernel_launches++;
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(osml::HostStager::instance().copy(ix->device, chunks, stream));
     return OSML_KNN_OK;
 }
 
@@ -237,14 +261,22 @@ int upload_rows(osml_knn_index* ix, const void* host, int layout, int64_t rows, 
     const size_t es = dtype_size(ix->dtype);
     const int64_t nr = r1 - r0;
     char* out = dst.as<char>() + (size_t)r0 * cols * es;
+    const size_t bytes = (size_t)nr * cols * es;
+    const bool staged = ix->opt_stager && bytes >= ((size_t)2 << 20) && osml::is_pageable_host(host);
     if (layout == OSML_KNN_ROW_MAJOR || rows == 1 || cols == 1) {
-        CUDA_TRY(cudaMemcpyAsync(out, static_cast<const char*>(host) + (size_t)r0 * cols * es, (size_t)nr * cols * es,
-                                 cudaMemcpyHostToDevice, stream));
+        const char* src = static_cast<const char*>(host) + (size_t)r0 * cols * es;
+        if (staged) return staged_copy_rowmajor(ix, src, out, bytes, stream);
+        CUDA_TRY(cudaMemcpyAsync(out, src, bytes, cudaMemcpyHostToDevice, stream));
         return OSML_KNN_OK;
     }
     char* st = ix->stage.as<char>() + (size_t)r0 * cols * es;      // [cols][nr], element (i, j) at j * nr + i
-    CUDA_TRY(cudaMemcpy2DAsync(st, (size_t)nr * es, static_cast<const char*>(host) + (size_t)r0 * es, (size_t)rows * es,
-                               (size_t)nr * es, (size_t)cols, cudaMemcpyHostToDevice, stream));
+    if (staged) {
+        int rc = staged_copy_colmajor(ix, static_cast<const char*>(host), rows, cols, r0, r1, es, st, stream);
+        if (rc != OSML_KNN_OK) return rc;
+    } else {
+        CUDA_TRY(cudaMemcpy2DAsync(st, (size_t)nr * es, static_cast<const char*>(host) + (size_t)r0 * es, (size_t)rows * es,
+                                   (size_t)nr * es, (size_t)cols, cudaMemcpyHostToDevice, stream));
+    }
     dim3 block(32, 8), grid((unsigned)((nr + 31) / 32), (unsigned)((cols + 31) / 32));
     switch (es) {
         case 1: transpose_colmajor_kernel<uint8_t><<<grid, block, 0, stream>>>((const uint8_t*)st, (uint8_t*)out, nr, cols); break;
@@ -255,6 +287,15 @@ int upload_rows(osml_knn_index* ix, const void* host, int layout, int64_t rows, 
     ix->stats.kernel_launches++;
     CUDA_TRY(cudaGetLastError());
     return OSML_KNN_OK;
+}
+
+// whole matrix (the train set at create)
+int upload_matrix(osml_knn_index* ix, const void* host, int layout, int64_t rows, int64_t cols, DeviceBuffer& dst,
+                  cudaStream_t stream) {
+    const size_t bytes = (size_t)rows * cols * dtype_size(ix->dtype);
+    CUDA_TRY(dst.reserve(bytes));
+    if (layout != OSML_KNN_ROW_MAJOR && rows > 1 && cols > 1) CUDA_TRY(ix->stage.reserve(bytes));
+    return upload_rows(ix, host, layout, rows, cols, 0, rows, dst, stream);
 }
 
 template <typename T>
@@ -510,7 +551,7 @@ int neighbours(osml_knn_index* ix, const void* d_queries, int64_t q, void* out_d
         tl.sum_order = ix->sum_order; tl.index_base = ix->index_base; tl.slack = ix->slack;
         tl.opt_epi_warps = ix->opt_epi_warps; tl.opt_nseg = ix->opt_nseg; tl.debug = ix->debug; tl.counters = ix->counters;
         tl.opt_smem_lists = ix->opt_smem_lists; tl.opt_cta_group = ix->opt_cta_group; tl.opt_active = ix->opt_active; tl.opt_precision = ix->opt_precision; tl.opt_wide_pair = ix->opt_wide_pair; tl.opt_kprime = ix->opt_kprime; tl.opt_hot = ix->opt_hot; tl.opt_live = ix->opt_live;
-        tl.before_wait = ix->before_wait; tl.first_block = ix->first_block;
+        tl.before_block = ix->before_block; tl.block_ends = ix->block_ends.data(); tl.n_blocks = (int)ix->block_ends.size();
         int64_t fallback = 0, launches = 0;
         std::string err;
         int rc = osml::tensor_neighbours(ix->tensor, tl, d_queries, q, out_d, out_i, stream, &fallback, &launches, &err,
@@ -759,26 +800,41 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
     CUDA_TRY(ix->nn_d.reserve((size_t)q * ksel * ix->dist_size()));
     CUDA_TRY(ix->nn_i.reserve((size_t)q * ksel * 8));
     CUDA_TRY(ix->pred.reserve((size_t)q * 8));
-    // Pipelined upload: queries are independent, so a large matrix goes up in two blocks.  The first is one full wave of
-    // K1 work items (sm_count x 128 queries: every CTA pair sweeps one tile pair, nothing is split); the rest is copied on
-    // a second stream once the first block's kernels are queued, i.e. under its K1, instead of in front of everything.
-    // Smaller calls whose upload is worth hiding go up in two halves: K1 cuts either half into enough train
-    // segments to fill the machine, so the split costs a few list warm-ups and hides half of the copy.
+    // Pipelined upload: queries are independent, so a large matrix goes up in blocks and every block but the first is
+    // copied on a second stream once the block in front of it has its kernels queued, i.e. under that block's K1 instead
+    // of in front of everything.  A call of two waves of K1 work items or more: the first block is one full wave
+    // (sm_count x 128 queries: every CTA pair sweeps one tile pair, nothing is split), the rest follows in one piece.
+    // Smaller calls whose upload is worth hiding go up in two equal blocks: K1 cuts either block into enough train
+    // segments to fill the machine (and the segments of a query share their thresholds), so the split costs a few list
+    // warm-ups and hides half of the copy.
     const int64_t wave = (int64_t)ix->sm_count * 128;
-    int64_t qa = q;
+    std::vector<int64_t> ends;
     if (ix->opt_pipeline && wave > 0) {
-        if (q >= 2 * wave) qa = wave;
+        if (q >= 2 * wave) ends = {wave, q};
         else if (q >= 4096 && (size_t)q * ix->d * es >= ((size_t)4 << 20)) {
-            // ... but only where the copy is a sizeable part of the call: ~40 GB/s up against ~1.2 PFLOP/s of filter.  Two
-            // halves hide half of the copy and pay for it with shorter sweeps (measured at 1M x 128 rows: 12 500 queries
-            // 3.3 ms in halves, 2.8 ms whole; 10 000 x 784 against 60 000 rows: 1.9 ms in halves, 2.0 ms whole)
+            // ... but only where the copy is a sizeable part of the call: ~40 GB/s up against ~1.2 PFLOP/s of filter
+            // (measured at 1M x 128 rows: 12 500 queries 3.3 ms in halves, 2.8 ms whole; 10 000 x 784 against 60 000
+            // rows: 1.9 ms in halves, 2.0 ms whole)
             const double copy_ms = (double)q * ix->d * es / 40e6;
             const double filter_ms = 2.0 * (double)ix->n * ix->d * (double)q / 1.2e12;
-            if (copy_ms >= 0.3 * filter_ms) qa = (q / 2 + 255) / 256 * 256;
+            if (copy_ms >= 0.3 * filter_ms) {
+                // (two blocks: measured at 10 000 x 784 queries against 60 000 rows, pinned: whole 1.50 ms, two blocks 1.33,
+                // three 1.38, four 1.49 -- every extra block restarts all its lists at once; option pipeline_blocks)
+                // a pageable matrix (a pandas frame) is bound by its gathering into pinned memory, not by K1: three blocks
+                // leave a shorter tail behind the last copy (1.60 ms against 1.81 in two, same shape)
+                const bool slow_source = ix->opt_stager && osml::is_pageable_host(queries);
+                const int nb = ix->opt_pipeline_blocks > 1 ? std::min(ix->opt_pipeline_blocks, 16) : (slow_source ? 3 : 2);
+                const int64_t per = ((q + nb - 1) / nb + 255) / 256 * 256;
+                for (int64_t e = per; e < q; e += per) ends.push_back(e);
+                ends.push_back(q);
+            }
         }
-        if (qa < q && (!use_tensor_path(ix, std::min(qa, q - qa)) || is_int_dtype(ix->dtype))) qa = q;
+        int64_t smallest = q, prev = 0;
+        for (int64_t e : ends) { smallest = std::min(smallest, e - prev); prev = e; }
+        if (ends.size() > 1 && (!use_tensor_path(ix, smallest) || is_int_dtype(ix->dtype))) ends.clear();
     }
-    const bool pipelined = qa < q;
+    const bool pipelined = ends.size() > 1;
+    const int64_t qa = pipelined ? ends[0] : q;
     CUDA_TRY(cudaEventRecord(ix->ev0, ix->stream));
     auto transform_rows = [&](int64_t r0, int64_t r1) -> int {   // raw queries: Centering / Standardization in place
         if (!ix->has_q_transform) return OSML_KNN_OK;
@@ -790,32 +846,32 @@ int osml_knn_predict(osml_knn_index* ix, const void* queries, int layout, int64_
     if (pipelined) CUDA_TRY(cudaEventRecord(ix->ev_first, ix->stream));     // the second block's copy starts here
     rc = transform_rows(0, qa);
     if (rc != OSML_KNN_OK) return rc;
-    bool sent = false;
-    const std::function<int()> send_rest = [&]() -> int {
-        if (sent) return OSML_KNN_OK;
-        sent = true;
-        CUDA_TRY(cudaStreamWaitEvent(ix->copy_stream, ix->ev_first, 0));   // the first block keeps the whole link
-        int rc2 = upload_rows(ix, queries, layout, q, ix->d, qa, q, ix->queries, ix->copy_stream);
+    int sent = 1;                                   // blocks uploaded so far
+    const std::function<int(int)> send_block = [&](int b) -> int {
+        if (b != sent || b >= (int)ends.size()) return fail(OSML_KNN_ECUDA, "internal: query blocks out of order");
+        if (b == 1) CUDA_TRY(cudaStreamWaitEvent(ix->copy_stream, ix->ev_first, 0));   // the first block keeps the whole link
+        ++sent;
+        int rc2 = upload_rows(ix, queries, layout, q, ix->d, ends[b - 1], ends[b], ix->queries, ix->copy_stream);
         if (rc2 != OSML_KNN_OK) return rc2;
         CUDA_TRY(cudaEventRecord(ix->ev_copy, ix->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(ix->stream, ix->ev_copy, 0));
-        return transform_rows(qa, q);
+        return transform_rows(ends[b - 1], ends[b]);
     };
     if (pipelined) {
-        ix->before_wait = &send_rest;
-        ix->first_block = qa;
+        ix->before_block = &send_block;
+        ix->block_ends = ends;
     }
     rc = predict_device_impl(ix, ix->queries.ptr, q, task, ix->pred.as<double>(), ix->nn_i.as<int64_t>(), ix->nn_d.ptr,
                              ix->stream);
-    ix->before_wait = nullptr;
-    ix->first_block = 0;
+    ix->before_block = nullptr;
+    ix->block_ends.clear();
     if (rc != OSML_KNN_OK) {
         // the caller's buffer must not be read after we return: uploads may still be in flight on either stream
         cudaStreamSynchronize(ix->stream);
-        if (sent) cudaStreamSynchronize(ix->copy_stream);
+        if (sent > 1) cudaStreamSynchronize(ix->copy_stream);
         return rc;
     }
-    if (pipelined && !sent) return fail(OSML_KNN_ECUDA, "internal: the second block of queries was never uploaded");
+    if (pipelined && sent != (int)ends.size()) return fail(OSML_KNN_ECUDA, "internal: not every block of queries was uploaded");
     CUDA_TRY(cudaMemcpyAsync(out_pred, ix->pred.ptr, (size_t)q * 8, cudaMemcpyDeviceToHost, ix->stream));
     if (out_idx) CUDA_TRY(cudaMemcpyAsync(out_idx, ix->nn_i.ptr, (size_t)q * ksel * 8, cudaMemcpyDeviceToHost, ix->stream));
     if (out_dist)
@@ -1033,6 +1089,8 @@ int osml_knn_set_option(osml_knn_index* ix, const char* name, double value) {
     if (key == "hot") { ix->opt_hot = (int)value; return OSML_KNN_OK; }
     if (key == "live") { ix->opt_live = (int)value; return OSML_KNN_OK; }
     if (key == "query_block") { ix->query_block = (int64_t)value; return OSML_KNN_OK; }
+    if (key == "stager") { ix->opt_stager = value != 0.0; return OSML_KNN_OK; }
+    if (key == "pipeline_blocks") { ix->opt_pipeline_blocks = (int)value; return OSML_KNN_OK; }
     if (key == "pipeline") { ix->opt_pipeline = value != 0.0; return OSML_KNN_OK; }
     return fail(OSML_KNN_EINVAL, "unknown option: " + key);
 }

@@ -97,6 +97,7 @@ struct TcParams {
     float* cand_thr;     // [qpad][nslot]: every row the slot dropped has score <= this (-inf: nothing dropped)
     int nhot;            // pair kernel, split items: segments 0 .. nhot-1 interleave over tiles [0, thot) (the small-norm rows,
     int thot;            //    where the neighbours are); the others are contiguous runs of what follows (see TcItemIter)
+    int live_all;        // whole-sweep items follow the gate too (their two column halves share it)
     unsigned int* gate;  // [qpad] pair kernel, split items: the best list threshold any slot of the query has proven so far,
                          //    order-preserving bits (tc_gate_enc); 0 = none yet
     const float* h;      // [npad] 0.5*|t^|^2 (+inf for padding rows)
@@ -1190,7 +1191,7 @@ knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 // gate, see tc_gate_enc) and keeps following it, one relaxed load per tile, issued in front of the wait
                 // for the accumulator; its own threshold is published whenever it has grown.
                 const size_t q = (size_t)qt * kTcBM + m;
-                const bool live = p.gate != nullptr && (nsg > 1 || (p.nseg > 1 && wi.qp >= p.nq_single));       // warp-uniform
+                const bool live = p.gate != nullptr && (p.live_all || nsg > 1 || (p.nseg > 1 && wi.qp >= p.nq_single));   // warp-uniform
                 unsigned int* const gate_addr = p.gate + q;
                 list.reset(-INFINITY, p.kactive);
                 if (live) list.raise_gate(tc_gate_dec(tc_gate_load(gate_addr)));
@@ -1688,10 +1689,12 @@ struct TensorLaunch {
     int opt_wide_pair = 1;   // 0 = rows too wide for the resident-tile pair kernel go to the single-CTA kernel (A/B)
     int debug = 0;
     int counters = 0;        // 1 = the CTA-pair kernel records where its issuer / epilogue warps wait (printed to stderr)
-    // host work to issue once the first block's kernels are queued (the pipelined osml_knn_predict uploads the rest of
-    // the queries here, so the copy runs under the first block's K1); 0 = ok, else a status
-    const std::function<int()>* before_wait = nullptr;
-    int64_t first_block = 0; // > 0: the first block of the call has this many queries (the rest is not on the device yet)
+    // A pipelined host call hands over its queries in blocks: block b covers queries [block_ends[b-1], block_ends[b]) and
+    // only block 0 is on the device when the search starts.  before_block(b), b >= 1, runs once block b-1's kernels are
+    // queued: the caller uploads block b there (under block b-1's K1) and makes `stream` wait for it; 0 = ok, else a status.
+    const std::function<int(int)>* before_block = nullptr;
+    const int64_t* block_ends = nullptr;
+    int n_blocks = 0;
     // one byte per query of the call (device, nullable): non-zero = this query must go to the exact direct kernel whatever
     // the completeness proof says (integer matrices: a query outside the range in which numpy's arithmetic cannot wrap)
     const unsigned char* q_force = nullptr;
@@ -2011,7 +2014,8 @@ inline int tc_filter_block(TensorState& st, const TensorLaunch& tl, const X* d_q
     p.cand_val = sc.cand_val.as<float>(); p.cand_idx = sc.cand_idx.as<int>();
     p.cand_thr = sc.cand_thr.as<float>();
     p.nhot = nhot; p.thot = thot;
-    p.gate = (tc_cta_group == 2 && nseg > 1 && tl.opt_live != 0) ? sc.gate.as<unsigned int>() : nullptr;
+    p.live_all = tl.opt_live == 2 ? 1 : 0;
+    p.gate = (tc_cta_group == 2 && (nseg > 1 || p.live_all) && tl.opt_live != 0) ? sc.gate.as<unsigned int>() : nullptr;
     p.h = st.half_norm.as<float>(); p.hmin8 = st.hmin8.as<float>(); p.hblk = st.hblk.as<float>();
     p.debug = OSML_TC_DEBUG ? tl.debug : 0;
     p.counters = tl.counters;
@@ -2169,17 +2173,18 @@ inline int tensor_neighbours_typed(TensorState& st, const TensorLaunch& tl, cons
     if (rc) return rc;
     st.filter_ms = 0.0;
     st.filter_launches = 0;
+    const bool blocks_given = tl.n_blocks > 1 && tl.block_ends != nullptr && tl.before_block && *tl.before_block;
     if (!st.usable) {                       // non-finite train rows: the filter's bounds do not hold
-        if (tl.before_wait && *tl.before_wait) {
-            rc = (*tl.before_wait)();
+        for (int b = 1; blocks_given && b < tl.n_blocks; ++b) {
+            rc = (*tl.before_block)(b);
             if (rc) return rc;
         }
         *fallback += q;
         return direct(d_queries, q, out_d, out_i);
     }
     // Blocks of queries are queued back to back and the host waits once, at the end, for the count of unproven queries
-    // of the whole call.  With a first_block the caller's before_wait hook runs as soon as that block is queued: the
-    // pipelined osml_knn_predict uploads the rest of the queries there (and makes `stream` wait for them).
+    // of the whole call.  The blocks are the caller's (a pipelined osml_knn_predict: see TensorLaunch::before_block), cut
+    // further where one exceeds 131 072 queries.
     const int64_t block = 131072;
     const int ksel = tl.k + 1;
     const X* dq = static_cast<const X*>(d_queries);
@@ -2187,20 +2192,20 @@ inline int tensor_neighbours_typed(TensorState& st, const TensorLaunch& tl, cons
     rc = tc_begin_unproven_list(st, 0, q, stream, err);
     if (rc) return rc;
     st.ev_k1_used = 0;
+    const int nb = blocks_given ? tl.n_blocks : 1;
     int64_t q0 = 0;
-    if (tl.first_block > 0 && tl.first_block < q) {
-        rc = tc_filter_block<X>(st, tl, dq, tl.first_block, od, out_i, stream, launches, err, 0, 0);
-        if (rc) return rc;
-        q0 = tl.first_block;
-    }
-    if (tl.before_wait && *tl.before_wait) {
-        rc = (*tl.before_wait)();
-        if (rc) return rc;
-    }
-    for (; q0 < q; q0 += block) {
-        const int64_t qb = std::min(block, q - q0);
-        rc = tc_filter_block<X>(st, tl, dq + q0 * tl.d, qb, od + q0 * ksel, out_i + q0 * ksel, stream, launches, err, 0, q0);
-        if (rc) return rc;
+    for (int b = 0; b < nb; ++b) {
+        if (b > 0) {
+            rc = (*tl.before_block)(b);
+            if (rc) return rc;
+        }
+        const int64_t q1 = blocks_given ? std::min(q, tl.block_ends[b]) : q;
+        for (; q0 < q1; q0 += block) {
+            const int64_t qb = std::min(block, q1 - q0);
+            rc = tc_filter_block<X>(st, tl, dq + q0 * tl.d, qb, od + q0 * ksel, out_i + q0 * ksel, stream, launches, err, 0, q0);
+            if (rc) return rc;
+        }
+        q0 = q1;
     }
     if (OSML_TC_DEBUG && tl.debug) return 0;
     return tc_resolve_unproven<X>(st, tl, dq, q, od, out_i, stream, fallback, launches, err, direct, 0);

@@ -357,20 +357,23 @@ def test_pipelined_upload_boundaries(extra):
     assert launches == (2 if q >= 2 * sms * 128 else 1)
 
 
-def test_small_calls_upload_in_two_halves():
-    """Below two waves of queries a call of 4 MB and more is uploaded in two halves (the second under the first half's
-    K1); smaller calls go up at once.  Same bits as the unpipelined call either way."""
+def test_small_calls_upload_in_equal_blocks():
+    """Below two waves of queries a call of 4 MB and more is uploaded in equal blocks (two, or what the pipeline_blocks
+    option says; every block but the first under the K1 of the block in front of it); smaller calls go up at once.  Same
+    bits as the unpipelined call either way."""
     rng = np.random.default_rng(81)
     n, d, k = 8192, 160, 5
     train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
     labels = rng.integers(0, 4, n)
-    for q, launches in ((9001, 2), (4100, 1), (700, 1)):          # 5.8 MB, 2.6 MB, 0.4 MB of float32 queries
+    # 5.8, 4.5, 2.6, 0.4 MB of pageable queries (three blocks by default; pinned memory: two)
+    for q, launches, blocks in ((9001, 3, 0), (9001, 4, 4), (7000, 2, 2), (4100, 1, 0), (700, 1, 4)):
         test = rng.standard_normal((q, d), dtype=np.float32)
         out = []
         for pipeline in (1, 0):
             ix = _native.Index(train, labels, k, 1, 1e-8)
             ix.set_option('path', _native.PATH_TENSOR)
             ix.set_option('pipeline', pipeline)
+            ix.set_option('pipeline_blocks', blocks)
             out.append(ix.predict(test, _native.CLASSIFICATION, return_neighbours=True))
             assert ix.stats()['last_filter_launches'] == (launches if pipeline else 1)
             ix.close()
