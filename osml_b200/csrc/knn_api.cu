@@ -212,14 +212,14 @@ struct DeviceGuard {
 // Pageable host memory goes through the pinned staging ring (host_stager.cuh) from 2 MB up: chunks of about a megabyte,
 // gathered by a few threads, one cudaMemcpyAsync each.  `dev` receives `bytes` contiguous bytes; piece `i` of them comes
 // from host address src(i_offset) -- contiguous for row-major input, one column segment after the other otherwise.
-int staged_copy_rowmajor(osml_knn_index* ix, const char* host, char* dev, size_t bytes, cudaStream_t stream) {
+int staged_copy_rowmajor(int device, const char* host, char* dev, size_t bytes, cudaStream_t stream) {
     std::vector<osml::HostStager::Chunk> chunks;
     for (size_t off = 0; off < bytes; off += osml::HostStager::kSlotBytes) {
         const size_t nb = std::min(osml::HostStager::kSlotBytes, bytes - off);
         const char* src = host + off;
         chunks.push_back({dev + off, nb, [src, nb](char* slot) { memcpy(slot, src, nb); }});
     }
-    CUDA_TRY(osml::HostStager::instance().copy(ix->device, chunks, stream));
+    CUDA_TRY(osml::HostStager::instance().copy(device, chunks, stream));
     return OSML_KNN_OK;
 }
 
@@ -265,7 +265,7 @@ int upload_rows(osml_knn_index* ix, const void* host, int layout, int64_t rows, 
     const bool staged = ix->opt_stager && bytes >= ((size_t)2 << 20) && osml::is_pageable_host(host);
     if (layout == OSML_KNN_ROW_MAJOR || rows == 1 || cols == 1) {
         const char* src = static_cast<const char*>(host) + (size_t)r0 * cols * es;
-        if (staged) return staged_copy_rowmajor(ix, src, out, bytes, stream);
+        if (staged) return staged_copy_rowmajor(ix->device, src, out, bytes, stream);
         CUDA_TRY(cudaMemcpyAsync(out, src, bytes, cudaMemcpyHostToDevice, stream));
         return OSML_KNN_OK;
     }
@@ -1027,7 +1027,14 @@ int osml_knn_column_transform(int device, const void* in, int dtype, int layout,
         (e = d_shift.reserve((size_t)d * out_es)) != cudaSuccess ||
         (denom && (e = d_denom.reserve((size_t)d * out_es)) != cudaSuccess))
         return done(fail(e == cudaErrorMemoryAllocation ? OSML_KNN_ENOMEM : OSML_KNN_ECUDA, cudaGetErrorString(e)));
-    if ((e = cudaMemcpy(d_in.ptr, in, elems * in_es, cudaMemcpyHostToDevice)) != cudaSuccess ||
+    // the matrix goes up as one flat run of bytes whatever its layout (the kernel reads either); pageable memory -- a
+    // frame's values -- through the pinned staging ring (host_stager.cuh)
+    if (elems * in_es >= ((size_t)2 << 20) && osml::is_pageable_host(in)) {
+        int rc = staged_copy_rowmajor(device, static_cast<const char*>(in), d_in.as<char>(), elems * in_es, nullptr);
+        if (rc != OSML_KNN_OK) return done(rc);
+        e = cudaSuccess;
+    } else e = cudaMemcpy(d_in.ptr, in, elems * in_es, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess ||
         (e = cudaMemcpy(d_shift.ptr, shift, (size_t)d * out_es, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (denom && (e = cudaMemcpy(d_denom.ptr, denom, (size_t)d * out_es, cudaMemcpyHostToDevice)) != cudaSuccess))
         return done(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
