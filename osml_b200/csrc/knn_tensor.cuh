@@ -390,7 +390,10 @@ __device__ __forceinline__ void tc_gate_publish(unsigned int* addr, float thr) {
 }
 
 constexpr int kTcHSlots = 8;          // ring of per-tile h blocks in the pair kernel
-constexpr int kTcBufCap = 16;         // buffered candidates per thread; a flush is forced above kTcBufCap - 8
+#ifndef OSML_TC_BUFCAP
+#define OSML_TC_BUFCAP 16
+#endif
+constexpr int kTcBufCap = OSML_TC_BUFCAP;   // buffered candidates per thread; a flush is forced above kTcBufCap - 8
 
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
@@ -1405,6 +1408,13 @@ __device__ __forceinline__ void tc_exact_distances_seq4(const X* __restrict__ tr
     memset(&zero, 0, sizeof(V));
     const V* q0 = reinterpret_cast<const V*>(qrow) + sub * 2;
     const uint32_t src = (uint32_t)((lane & ~3) | ((sub + 3) & 3));      // the lane in front of this one in the chain
+    // kept opaque: the compiler would otherwise rebuild these from %tid and the kernel parameters on every trip
+    {
+        int* keep[] = {const_cast<int*>(&sub), const_cast<int*>(&nv), const_cast<int*>(&nfull), const_cast<int*>(&ntrip)};
+#pragma unroll
+        for (int* r : keep) asm volatile("mov.b32 %0, %0;" : "+r"(*r));
+        asm volatile("mov.b32 %0, %0;" : "+r"(*const_cast<uint32_t*>(&src)));
+    }
     for (int jb = j0; jb < j1; jb += 8) {
         const int j = jb + grp;
         const bool valid = j < j1;                   // idle groups re-read the first row of the pass (same cache lines)
