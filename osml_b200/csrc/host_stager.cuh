@@ -59,12 +59,7 @@ public:
         job_chunks_ = &chunks;
         next_.store(0);
         confirmed_.store(-kSlots);                   // chunks -kSlots .. -1: whatever earlier copies left in the slots
-        {
-            std::lock_guard<std::mutex> g(m_);
-            pending_workers_ = nworkers_;
-            ++generation_;
-        }
-        cv_work_.notify_all();
+        start_workers(0);
         for (int c = 0; c < n && e == cudaSuccess; ++c) {
             // confirm old DMAs so that the workers can run kAhead chunks ahead (they finished long ago: the DMA is
             // faster than the gathering, so these waits return at once)
@@ -73,6 +68,7 @@ public:
                 e = cudaEventSynchronize(events_[((o % kSlots) + kSlots) % kSlots]);
                 confirmed_.store(o + 1, std::memory_order_release);
             }
+            if (e != cudaSuccess) break;             // (a worker waiting for this confirmation is released below)
             while (!filled_[c].load(std::memory_order_acquire)) __builtin_ia32_pause();
             char* src = static_cast<char*>(ring_) + (size_t)(c % kSlots) * kSlotBytes;
             if (e == cudaSuccess) e = cudaMemcpyAsync(chunks[c].device_dst, src, chunks[c].bytes, cudaMemcpyHostToDevice, stream);
@@ -82,14 +78,74 @@ public:
             abort_.store(true);
             confirmed_.store(n + kSlots, std::memory_order_release);
         }
-        std::unique_lock<std::mutex> g(m_);
-        cv_done_.wait(g, [&] { return pending_workers_ == 0; });
+        wait_workers();
+        abort_.store(false);
+        return e;
+    }
+
+    // The way back: device -> pageable host memory.  The calling thread issues one DMA per chunk into the ring and
+    // waits for each in order; the workers copy finished slots out to `drain`'s destination, so the page faults of a
+    // freshly allocated result array (most of the cost of a plain cudaMemcpy into one) are spread over threads and run
+    // under the DMA of the following chunks.
+    struct OutChunk {
+        const void* device_src;
+        size_t bytes;
+        std::function<void(const char*)> drain;
+    };
+
+    cudaError_t copy_out(int device, const std::vector<OutChunk>& chunks, cudaStream_t stream) {
+        std::lock_guard<std::mutex> job_guard(job_mutex_);
+        cudaError_t e = ensure(device);
+        if (e != cudaSuccess) return e;
+        const int n = (int)chunks.size();
+        if ((int)filled_size_ < n) { filled_.reset(new std::atomic<unsigned char>[n]); filled_size_ = n; }
+        if ((int)drained_size_ < n) { drained_.reset(new std::atomic<unsigned char>[n]); drained_size_ = n; }
+        for (int c = 0; c < n; ++c) { filled_[c].store(0, std::memory_order_relaxed); drained_[c].store(0, std::memory_order_relaxed); }
+        for (int s = 0; s < kSlots && e == cudaSuccess; ++s) e = cudaEventSynchronize(events_[s]);   // earlier copies have left the ring
+        if (e != cudaSuccess) return e;
+        out_chunks_ = &chunks;
+        next_.store(0);
+        start_workers(1);
+        int issued = 0, readied = 0;
+        while (readied < n) {
+            while (e == cudaSuccess && issued < n &&
+                   (issued < kSlots || drained_[issued - kSlots].load(std::memory_order_acquire))) {
+                char* dst = static_cast<char*>(ring_) + (size_t)(issued % kSlots) * kSlotBytes;
+                e = cudaMemcpyAsync(dst, chunks[issued].device_src, chunks[issued].bytes, cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess) e = cudaEventRecord(events_[issued % kSlots], stream);
+                ++issued;
+            }
+            if (e != cudaSuccess) break;
+            if (readied < issued) {
+                e = cudaEventSynchronize(events_[readied % kSlots]);
+                if (e != cudaSuccess) break;
+                filled_[readied].store(1, std::memory_order_release);      // the slot holds chunk `readied`
+                ++readied;
+            } else __builtin_ia32_pause();
+        }
+        if (e != cudaSuccess) {                      // let the workers run out without touching anything
+            abort_.store(true);
+            for (int c = 0; c < n; ++c) filled_[c].store(1, std::memory_order_release);
+        }
+        wait_workers();
         abort_.store(false);
         return e;
     }
 
 private:
     HostStager() = default;
+
+    void start_workers(int kind) {
+        std::lock_guard<std::mutex> g(m_);
+        job_kind_ = kind;
+        pending_workers_ = nworkers_;
+        ++generation_;
+        cv_work_.notify_all();
+    }
+    void wait_workers() {
+        std::unique_lock<std::mutex> g(m_);
+        cv_done_.wait(g, [&] { return pending_workers_ == 0; });
+    }
 
     cudaError_t ensure(int device) {
         if (pid_ != getpid()) {                      // first use, or a forked child (threads do not survive a fork)
@@ -128,14 +184,26 @@ private:
                 cv_work_.wait(g, [&] { return generation_ != seen; });
                 seen = generation_;
             }
-            const std::vector<Chunk>& chunks = *job_chunks_;
-            const int n = (int)chunks.size();
-            for (;;) {
-                const int c = next_.fetch_add(1);
-                if (c >= n) break;
-                while (confirmed_.load(std::memory_order_acquire) < c - kSlots + 1) __builtin_ia32_pause();
-                if (!abort_.load()) chunks[c].fill(static_cast<char*>(ring_) + (size_t)(c % kSlots) * kSlotBytes);
-                filled_[c].store(1, std::memory_order_release);
+            if (job_kind_ == 0) {                    // host -> device: gather chunks into free slots
+                const std::vector<Chunk>& chunks = *job_chunks_;
+                const int n = (int)chunks.size();
+                for (;;) {
+                    const int c = next_.fetch_add(1);
+                    if (c >= n) break;
+                    while (confirmed_.load(std::memory_order_acquire) < c - kSlots + 1) __builtin_ia32_pause();
+                    if (!abort_.load()) chunks[c].fill(static_cast<char*>(ring_) + (size_t)(c % kSlots) * kSlotBytes);
+                    filled_[c].store(1, std::memory_order_release);
+                }
+            } else {                                 // device -> host: copy landed slots out
+                const std::vector<OutChunk>& chunks = *out_chunks_;
+                const int n = (int)chunks.size();
+                for (;;) {
+                    const int c = next_.fetch_add(1);
+                    if (c >= n) break;
+                    while (!filled_[c].load(std::memory_order_acquire)) __builtin_ia32_pause();
+                    if (!abort_.load()) chunks[c].drain(static_cast<const char*>(ring_) + (size_t)(c % kSlots) * kSlotBytes);
+                    drained_[c].store(1, std::memory_order_release);
+                }
             }
             {
                 std::lock_guard<std::mutex> g(m_);
@@ -155,8 +223,10 @@ private:
     void* ring_ = nullptr;
     cudaEvent_t events_[kSlots] = {};
     int events_device_ = -1;
-    std::unique_ptr<std::atomic<unsigned char>[]> filled_;
-    size_t filled_size_ = 0;
+    std::unique_ptr<std::atomic<unsigned char>[]> filled_, drained_;
+    size_t filled_size_ = 0, drained_size_ = 0;
+    int job_kind_ = 0;
+    const std::vector<OutChunk>* out_chunks_ = nullptr;
     std::atomic<int> next_{0}, confirmed_{0};
     std::atomic<bool> abort_{false};
     const std::vector<Chunk>* job_chunks_ = nullptr;

@@ -1053,8 +1053,18 @@ int osml_knn_column_transform(int device, const void* in, int dtype, int layout,
         default: e = osml::launch_column_transform<uint64_t, double>(d_in.ptr, d_out.ptr, n, d, cm, d_shift.ptr, dn, nullptr); break;
     }
     if (e != cudaSuccess) return done(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
-    if ((e = cudaMemcpy(out, d_out.ptr, elems * out_es, cudaMemcpyDeviceToHost)) != cudaSuccess)
-        return done(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
+    // ... and comes back the same way: pageable results (a fresh numpy array) through the ring, copied out by the workers
+    if (elems * out_es >= ((size_t)2 << 20) && osml::is_pageable_host(out)) {
+        std::vector<osml::HostStager::OutChunk> chunks;
+        const size_t bytes = elems * out_es;
+        for (size_t off = 0; off < bytes; off += osml::HostStager::kSlotBytes) {
+            const size_t nb = std::min(osml::HostStager::kSlotBytes, bytes - off);
+            char* dst = static_cast<char*>(out) + off;
+            chunks.push_back({d_out.as<char>() + off, nb, [dst, nb](const char* slot) { memcpy(dst, slot, nb); }});
+        }
+        e = osml::HostStager::instance().copy_out(device, chunks, nullptr);
+    } else e = cudaMemcpy(out, d_out.ptr, elems * out_es, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return done(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
     return done(OSML_KNN_OK);
 }
 

@@ -49,6 +49,23 @@ def test_every_dtype_both_layouts_through_the_c_abi(dtype, order):
     assert _same(_native.column_transform(x, shift, None), to.centering_transform(x, mean))
 
 
+@pytest.mark.parametrize('dtype,n,d', [('float32', 60001, 20), ('float64', 300007, 3), ('int8', 900000, 3),
+                                         ('float32', 9, 60000)])
+@pytest.mark.parametrize('order', ['F', 'C'])
+def test_large_matrices_through_the_staging_ring(dtype, n, d, order):
+    """From 2 MB up a pageable matrix goes to the device -- and the result comes back -- through the ring of pinned slots
+    (host_stager.cuh: chunks of a megabyte, the last one ragged; int8 in, float64 out: only the way back is staged)."""
+    rng = np.random.default_rng(n + d)
+    x = (rng.standard_normal((n, d)) * 9).astype(dtype)
+    x = np.asfortranarray(x) if order == 'F' else np.ascontiguousarray(x)
+    mean, sd = to.standardization_fit(x)
+    shift, denom = to.shift_and_denominator(mean, sd, 1e-8)
+    want = to.standardization_transform(x, mean, sd, 1e-8)
+    for _ in range(2):                  # the ring is reused
+        got = _native.column_transform(x, shift, denom)
+        assert _same(got, want) and got.flags['F_CONTIGUOUS'] == want.flags['F_CONTIGUOUS']
+
+
 def test_degenerate_columns_and_nonfinite_values():
     x = np.asfortranarray(np.random.default_rng(3).standard_normal((300, 5)).astype(np.float32))
     x[:, 2] = 7.0                       # sd == 0: the reference divides by epsilon
