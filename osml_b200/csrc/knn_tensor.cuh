@@ -426,7 +426,8 @@ struct TcRegList {
     __device__ __forceinline__ void attach(uint32_t addr, uint32_t stride) {
         buf_addr = addr; buf_stride = stride; buf_shift = 31 - __clz((int)stride); cnt = 0; rd = 0;
     }
-    // empty slots hold -FLT_MAX, or a seed threshold proven elsewhere (values at or below it are never inserted)
+    // empty slots hold -FLT_MAX (or a seed threshold proven elsewhere: values at or below it are never inserted; the pair
+    // kernel uses the live gate instead and always resets to -FLT_MAX)
     // `active` <= KP entries take part; the others are parked at +FLT_MAX so that they are never the minimum (a list
     // length between the powers of two the slot packing allows: fewer entries -> higher threshold -> fewer hits)
     __device__ __forceinline__ void reset(float seed = -INFINITY, int active = KP) {
@@ -867,12 +868,12 @@ constexpr int kTcBHalfBytes = (kTcBN / 2) * 128;      // 16 KB: this CTA's half 
 // pairs 0 .. nq_single-1, then the split pairs' interleaved segments (tiles seg, seg + nseg, ...: every segment sees
 // the whole range of row norms in ascending order), numbered segment-major -- all pairs' segment 0, then all pairs'
 // segment 1, ... -- so that by the time a later segment of a query starts its earlier segments have usually finished
-// and their thresholds seed its lists.  Every item writes candidate slot `slot` of its queries (x halves).
-// Hot-first split (nhot < nseg): the filter copy is sorted by row norm and score = q.t - h, so the rows that end up in a
-// query's lists sit overwhelmingly in the first tiles.  Interleaving ALL segments hands every item its own share of
-// those rows, i.e. its own dense list warm-up.  Instead the segments that make up the first wave of items interleave
-// over the first thot tiles only, and the later ones take contiguous runs of the rest: by the time they start the
-// query's gate (see tc_gate_enc) is settled and almost nothing they see passes it.
+// and the query's gate (see tc_gate_enc) already holds what they proved.  Every item writes candidate slot `slot` of
+// its queries (x halves).
+// Hot-first split (option `hot`, nhot < nseg; not the default -- measured, see tc_filter_block): the filter copy is sorted
+// by row norm and score = q.t - h, so the rows that end up in a query's lists sit overwhelmingly in the first tiles, and
+// interleaving ALL segments hands every item its own share of those rows.  With nhot < nseg the first nhot segments
+// interleave over the first thot tiles only and the later ones take contiguous runs of the rest behind a settled gate.
 // (Measured and dropped: cutting the pair-major tile sequence into one contiguous run per CTA pair.  It balances
 // perfectly and makes sweeps as long as possible, but a run in the middle of the norm-sorted order never sees the
 // small-norm rows that settle the thresholds: 10-60 % slower on every shape tried.)
@@ -905,9 +906,10 @@ struct TcItemIter {
 
 // kWide (rows too long for a resident query tile next to two whole half-tile stages: D > 192): the ring works at K-block
 // granularity instead -- a stage holds [this CTA's 128 x 64 query block][its 128 x 64 half of the train block], one
-// barrier round trip per K block, one issuer thread (a tile takes thousands of MMA cycles, its bookkeeping is noise).
+// barrier round trip per K block, K blocks alternating between two issuer threads (the round trips of a lone issuer were
+// tensor-pipe idle time: see the issuers below).
 // Everything else -- the CTA pair's M = 256 MMA that halves the L2 -> shared-memory traffic per FLOP of the single-CTA
-// kernel, the staged epilogue with early TMEM release, the h ring, threshold seeding -- is the same code.
+// kernel, the staged epilogue with early TMEM release, the h ring, the live gates -- is the same code.
 template <int KP, bool kWide>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
