@@ -141,8 +141,11 @@ int osml_knn_merge_predict_packed_device(osml_knn_index* index, const void* d_re
 
 /* Options: "path" (enum osml_knn_path), "slack" (extra candidates the tensor filter keeps beyond k+1),
  * "query_block" (queries per internal batch), "pipeline" (1 = default: osml_knn_predict uploads a query matrix of
- * 4 MB or more in two blocks, the second under the first block's filter kernel; 0 = one block).
- * Unknown name -> EINVAL. */
+ * 4 MB or more in blocks, every block but the first under the filter kernel of the block in front of it; 0 = one block),
+ * "pipeline_blocks" (0 = default: two blocks from pinned memory, three from pageable memory; n = that many),
+ * "stager" (1 = default: pageable host matrices of 2 MB or more go up through a ring of pinned staging slots filled
+ * by worker threads; 0 = plain cudaMemcpyAsync).  The remaining names are tuning knobs of the tensor filter for
+ * experiments.  Unknown name -> EINVAL. */
 int osml_knn_set_option(osml_knn_index* index, const char* name, double value);
 
 int osml_knn_get_stats(osml_knn_index* index, osml_knn_stats* out);
