@@ -58,7 +58,7 @@ enum osml_knn_status {
 
 /* which distance/selection kernel osml_knn_predict uses */
 enum osml_knn_path {
-    OSML_KNN_PATH_AUTO = 0,    /* tensor filter for float32 / float64 data with at least 16384 rows, built once 128 queries
+    OSML_KNN_PATH_AUTO = 0,    /* tensor filter for float32 / float64 data with at least 4096 rows, built once 128 queries
                                   have been asked for; direct otherwise, and after a call most of whose queries the
                                   filter could not prove (tie-ridden data) */
     OSML_KNN_PATH_DIRECT = 1,  /* K2: exact direct-difference kernel on CUDA cores, any dtype */

@@ -429,6 +429,8 @@ int launch_direct(osml_knn_index* ix, const void* d_queries, int64_t q, void* ou
 bool is_int_dtype(int dtype) { return dtype != OSML_KNN_F32 && dtype != OSML_KNN_F64; }
 
 // dtype the tensor path computes in: the matrix's own for floats, float64 (an exact shadow) for integers
+constexpr int64_t kAutoTensorRows = 4096;      // path = auto: smaller training sets stay on the direct kernel
+
 int tensor_dtype(const osml_knn_index* ix) { return is_int_dtype(ix->dtype) ? (int)OSML_KNN_F64 : ix->dtype; }
 
 bool use_tensor_path(const osml_knn_index* ix, int64_t q) {
@@ -442,7 +444,10 @@ bool use_tensor_path(const osml_knn_index* ix, int64_t q) {
     // about what the direct kernel needs for 150 queries, so it is built once that many have been asked for.  Data on
     // which the completeness proof keeps failing (massive exact ties) would pay for the filter AND the direct kernel:
     // after such a call auto stays on the direct kernel.
-    if (ix->n < 16384 || ix->auto_direct) return false;
+    // (round 2, after the work split for small calls: the filter also wins from 4096 rows on -- 4096 x 128: 0.11 / 0.12 /
+    // 0.14 ms for 16 / 1024 / 8192 queries against 0.12 / 0.32 / 1.08 ms; 8192 x 784, 8192 queries: 0.38 vs 12.5 ms; at
+    // 2048 rows only from ~1000 queries on)
+    if (ix->n < kAutoTensorRows || ix->auto_direct) return false;
     return ix->tensor.ready || q + ix->seen_queries >= 128;
 }
 
@@ -680,7 +685,7 @@ int osml_knn_create(osml_knn_index** out, int device, const void* train, int dty
         return cleanup(fail(e == cudaErrorMemoryAllocation ? OSML_KNN_ENOMEM : OSML_KNN_ECUDA, cudaGetErrorString(e)));
     if ((e = cudaStreamSynchronize(ix->stream)) != cudaSuccess) return cleanup(fail(OSML_KNN_ECUDA, cudaGetErrorString(e)));
     ix->stage.release();
-    if (is_int_dtype(dtype) && osml::tensor_path_supported(OSML_KNN_F64, n, d, k) && n >= 16384) {
+    if (is_int_dtype(dtype) && osml::tensor_path_supported(OSML_KNN_F64, n, d, k) && n >= kAutoTensorRows) {
         rc = int_scan_train(ix);          // can the tensor path serve this integer matrix? (value range, see int_type_limit)
         if (rc != OSML_KNN_OK) return cleanup(rc);
     }

@@ -52,7 +52,7 @@ def test_tie_light_integer_data_is_proven_by_the_filter():
     train = np.asfortranarray(rng.integers(0, 40001, (n, d)).astype(np.int32))
     test = rng.integers(0, 40001, (q, d)).astype(np.int32)
     labels = rng.standard_normal(n)
-    ix = _native.Index(train, labels, k, 1, 1e-8)            # auto: n >= 16384 and the range cannot wrap -> filter
+    ix = _native.Index(train, labels, k, 1, 1e-8)            # auto: n >= 4096 and the range cannot wrap -> filter
     pred, idx, dist = ix.predict(test, _native.REGRESSION, return_neighbours=True)
     stats = ix.stats()
     ix.close()

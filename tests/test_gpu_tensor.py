@@ -578,3 +578,31 @@ def test_k_beyond_the_filter_stays_on_the_direct_kernel():
     assert ix.stats()['tensor_queries'] == 0
     ix.close()
     parity.assert_matches_oracle(pred, idx, dist, train, labels, test, k, 1, 'regression')
+
+
+@pytest.mark.parametrize('n,d,q,k', [(4096, 128, 1500, 10), (5000, 20, 300, 7), (9000, 300, 700, 10)])
+def test_auto_takes_the_filter_from_4096_rows_on_and_small_calls_use_one_wave_of_segments(n, d, q, k):
+    """path = auto: a fitted float index of 4096 rows or more answers through the tensor filter once 128 queries have
+    been asked for (smaller ones stay on the direct kernel).  Calls of a few query-tile pairs are cut into as many
+    segments as fit one wave of work items (up to 32 for one or two pairs); the result is the direct kernel's, bit for
+    bit, and the oracle's."""
+    rng = np.random.default_rng(n + q)
+    train = np.asfortranarray(rng.standard_normal((n, d), dtype=np.float32))
+    test = rng.standard_normal((q, d), dtype=np.float32)
+    labels = rng.integers(0, 6, n)
+    ix = _native.Index(train, labels, k, 1, 1e-8)
+    auto = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    assert ix.stats()['tensor_queries'] == q
+    few = ix.predict(test[:40], _native.CLASSIFICATION, return_neighbours=True)          # one pair: the most segments
+    ix.set_option('path', _native.PATH_DIRECT)
+    direct = ix.predict(test, _native.CLASSIFICATION, return_neighbours=True)
+    ix.close()
+    assert all(np.array_equal(a, b) for a, b in zip(auto, direct))
+    assert all(np.array_equal(a, b[:40]) for a, b in zip(few, direct))
+    sample = rng.choice(q, 48, replace=False)
+    parity.assert_matches_oracle(auto[0][sample], auto[1][sample], auto[2][sample], train, labels,
+                                 np.ascontiguousarray(test[sample]), k, 1, 'classification')
+    small = _native.Index(train[:4000], labels[:4000], k, 1, 1e-8)                        # below the threshold: direct
+    small.predict(test, _native.CLASSIFICATION)
+    assert small.stats()['tensor_queries'] == 0
+    small.close()
