@@ -69,7 +69,25 @@ public:
                 confirmed_.store(o + 1, std::memory_order_release);
             }
             if (e != cudaSuccess) break;             // (a worker waiting for this confirmation is released below)
-            while (!filled_[c].load(std::memory_order_acquire)) __builtin_ia32_pause();
+            // while chunk c is still being gathered the calling thread gathers one itself (it is one more core at work;
+            // the DMA engine is the faster side and has the ring's slots to draw from)
+            while (e == cudaSuccess && !filled_[c].load(std::memory_order_acquire)) {
+                int mine = next_.load();
+                // only a chunk whose slot was last used by an ISSUED chunk (mine - kSlots < c): that DMA can be waited for here
+                if (mine >= n || mine - kSlots >= c || !next_.compare_exchange_strong(mine, mine + 1)) {
+                    __builtin_ia32_pause();
+                    continue;
+                }
+                while (e == cudaSuccess && confirmed_.load(std::memory_order_relaxed) < mine - kSlots + 1) {
+                    const int o = confirmed_.load(std::memory_order_relaxed);
+                    e = cudaEventSynchronize(events_[((o % kSlots) + kSlots) % kSlots]);
+                    confirmed_.store(o + 1, std::memory_order_release);
+                }
+                if (e != cudaSuccess) break;
+                chunks[mine].fill(static_cast<char*>(ring_) + (size_t)(mine % kSlots) * kSlotBytes);
+                filled_[mine].store(1, std::memory_order_release);
+            }
+            if (e != cudaSuccess) break;
             char* src = static_cast<char*>(ring_) + (size_t)(c % kSlots) * kSlotBytes;
             if (e == cudaSuccess) e = cudaMemcpyAsync(chunks[c].device_dst, src, chunks[c].bytes, cudaMemcpyHostToDevice, stream);
             if (e == cudaSuccess) e = cudaEventRecord(events_[c % kSlots], stream);
