@@ -28,8 +28,9 @@ public:
     static constexpr size_t kSlotBytes = (size_t)1 << 20;
     static constexpr int kSlots = 16;
     static constexpr int kAhead = 8;                 // slots the workers may fill ahead of the chunk being issued
-    // gather threads ($OSML_STAGER_THREADS for experiments); the caller issues.  Measured on a 16-core B200 host, 31 MB
-    // column-major, whole predict call: 2 threads 1.60 ms, 3: 1.67, 4: 1.96, 6: 2.07, 8: 3.05 (driver's pageable path: 2.68)
+    // gather threads ($OSML_STAGER_THREADS for experiments); the caller issues every copy and gathers a chunk itself when
+    // it would otherwise wait.  Measured on a 16-core B200 host, 31 MB column-major, whole predict call, workers only:
+    // 2 threads 1.60 ms, 3: 1.67, 4: 1.96, 6: 2.07, 8: 3.05 (driver's pageable path: 2.68)
     static constexpr int kWorkers = 2;
 
     // One chunk: `fill(dst)` gathers `bytes` (<= kSlotBytes) of host data into the pinned slot `dst`; the slot then goes
